@@ -1,0 +1,181 @@
+"""BASELINE.json workloads C1..C5, written ONCE against an abstract namespace ``nd``.
+
+The same builder runs against three namespaces that expose the reference's names
+(``FCNN, SinActv, IVP, BundleIVP, DirichletBVP2D, IBVP1D, DirichletBVPSpherical, diff, spherical_laplacian``):
+
+* the unmodified reference (``tools/ref_shim.py``; only in the build container, to make ``tests/golden``),
+* the CPU oracle (``oracle/``; tests + ``bench.py`` baseline legs only),
+* the product (``neurodiffeq_b200``; traces the same callables symbolically and runs the CUDA kernels).
+
+so that parity tests read like the reference's own usage (README.md:74-130 of the reference).
+Coordinates are synthetic (``numpy.random.RandomState(seed)``, fp32-representable values) so that every
+implementation sees bit-identical inputs; sampling by the generator classes is tested separately.
+"""
+import math
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+Workload = namedtuple(
+    "Workload",
+    "name solver coord_names coord_ranges nets_spec make_nets make_conditions diff_eqs n_eq default_n flops_fwdjet "
+    "eq_param_index"
+)
+
+NU_BURGERS = 0.01 / math.pi
+
+
+def _fcnn_flops(widths, n_channels):
+    """F_fwdjet = 2*d0*h1 + C*2*(sum_{l>=2} h_{l-1} h_l + h_L*dout)."""
+    d0, h = widths[0], widths[1:]
+    rest = sum(a * b for a, b in zip(h[:-1], h[1:]))
+    return 2 * d0 * h[0] + n_channels * 2 * rest
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C1  Solver1D Lotka-Volterra, 2 x FCNN(1-32-32-1, SinActv)            (reference README.md:85-93)
+# ----------------------------------------------------------------------------------------------------------------------
+def _c1(nd):
+    def make_nets():
+        return [nd.FCNN(n_input_units=1, n_output_units=1, hidden_units=(32, 32), actv=nd.SinActv) for _ in range(2)]
+
+    def make_conditions():
+        return [nd.IVP(t_0=0.0, u_0=1.5), nd.IVP(t_0=0.0, u_0=1.0)]
+
+    def diff_eqs(u, v, t):
+        return [nd.diff(u, t) - (u - u * v), nd.diff(v, t) - (u * v - v)]
+
+    return Workload("c1_lotka_volterra", "Solver1D", ("t",), ((0.1, 12.0),),
+                    [((1, 32, 32, 1), "sin")] * 2, make_nets, make_conditions, diff_eqs, 2, 1024,
+                    2 * _fcnn_flops((1, 32, 32, 1), 2), None)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C2  Solver2D Laplace, DirichletBVP2D, FCNN(2-64-64-64-1, tanh)        (reference README.md:113-128)
+# ----------------------------------------------------------------------------------------------------------------------
+def _c2(nd):
+    def make_nets():
+        return [nd.FCNN(n_input_units=2, n_output_units=1, hidden_units=(64, 64, 64))]
+
+    def make_conditions():
+        return [nd.DirichletBVP2D(
+            x_min=0, x_min_val=lambda y: torch.sin(np.pi * y),
+            x_max=1, x_max_val=lambda y: 0,
+            y_min=0, y_min_val=lambda x: 0,
+            y_max=1, y_max_val=lambda x: 0,
+        )]
+
+    def diff_eqs(u, x, y):
+        return [nd.diff(u, x, order=2) + nd.diff(u, y, order=2)]
+
+    return Workload("c2_laplace2d", "Solver2D", ("x", "y"), ((0.0, 1.0), (0.0, 1.0)),
+                    [((2, 64, 64, 64, 1), "tanh")], make_nets, make_conditions, diff_eqs, 1, 16384,
+                    _fcnn_flops((2, 64, 64, 64, 1), 5), None)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C3  Solver2D Burgers, IBVP1D (Dirichlet-Dirichlet), FCNN(2-128-128-128-1, tanh)     
+# ----------------------------------------------------------------------------------------------------------------------
+def _c3(nd):
+    def make_nets():
+        return [nd.FCNN(n_input_units=2, n_output_units=1, hidden_units=(128, 128, 128))]
+
+    def make_conditions():
+        return [nd.IBVP1D(
+            x_min=-1, x_max=1, t_min=0,
+            t_min_val=lambda x: -torch.sin(np.pi * x),
+            x_min_val=lambda t: 0,
+            x_max_val=lambda t: 0,
+        )]
+
+    def diff_eqs(u, x, t):
+        return [nd.diff(u, t) + u * nd.diff(u, x) - NU_BURGERS * nd.diff(u, x, order=2)]
+
+    return Workload("c3_burgers", "Solver2D", ("x", "t"), ((-1.0, 1.0), (0.0, 1.0)),
+                    [((2, 128, 128, 128, 1), "tanh")], make_nets, make_conditions, diff_eqs, 1, 65536,
+                    _fcnn_flops((2, 128, 128, 128, 1), 4), None)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C4  SolverSpherical Poisson with spherical_laplacian, FCNN(3-64-64-64-1)  (reference tests/test_pde_spherical.py:103)
+# ----------------------------------------------------------------------------------------------------------------------
+def _c4(nd):
+    r0, r1 = 0.1, 3.0
+    k_q = 1.0 / (4 * math.pi)
+    v0 = k_q / r0 * math.erf(r0 / math.sqrt(2))
+    v1 = k_q / r1 * math.erf(r1 / math.sqrt(2))
+    norm = (2 * math.pi) ** 1.5
+
+    def make_nets():
+        return [nd.FCNN(n_input_units=3, n_output_units=1, hidden_units=(64, 64, 64))]
+
+    def make_conditions():
+        return [nd.DirichletBVPSpherical(r_0=r0, f=lambda th, ph: v0, r_1=r1, g=lambda th, ph: v1)]
+
+    def diff_eqs(u, r, th, ph):
+        return [nd.spherical_laplacian(u, r, th, ph) + torch.exp(-r ** 2 / 2) / norm]
+
+    return Workload("c4_spherical_poisson", "SolverSpherical", ("r", "theta", "phi"),
+                    ((r0, r1), (0.07, math.pi - 0.07), (0.0, 2 * math.pi)),
+                    [((3, 64, 64, 64, 1), "tanh")], make_nets, make_conditions, diff_eqs, 1, 32768,
+                    _fcnn_flops((3, 64, 64, 64, 1), 7), None)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C5  BundleSolver1D damped oscillator, 4 bundle params, ONE shared FCNN(5-64-64-2) with ith_unit  
+# ----------------------------------------------------------------------------------------------------------------------
+def _c5(nd):
+    def make_nets():
+        net = nd.FCNN(n_input_units=5, n_output_units=2, hidden_units=(64, 64))
+        return [net, net]
+
+    def make_conditions():
+        import warnings
+        conds = [nd.BundleIVP(t_0=0.0, bundle_param_lookup={"u_0": 2}),
+                 nd.BundleIVP(t_0=0.0, bundle_param_lookup={"u_0": 3})]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for i, c in enumerate(conds):
+                c.set_impose_on(i)
+        return conds
+
+    def diff_eqs(u, v, t, zeta, omega):
+        return [nd.diff(u, t) - v, nd.diff(v, t) + 2 * zeta * omega * v + omega ** 2 * u]
+
+    return Workload("c5_bundle_oscillator", "BundleSolver1D", ("t", "zeta", "omega", "u0", "v0"),
+                    ((0.0, 2 * math.pi), (0.05, 0.5), (0.5, 2.0), (-1.0, 1.0), (-1.0, 1.0)),
+                    [((5, 64, 64, 2), "tanh")], make_nets, make_conditions, diff_eqs, 2, 131072,
+                    _fcnn_flops((5, 64, 64, 2), 2), (0, 1))
+
+
+_BUILDERS = {"c1": _c1, "c2": _c2, "c3": _c3, "c4": _c4, "c5": _c5}
+NAMES = tuple(_BUILDERS)
+
+
+def build(nd, key):
+    """``nd`` = namespace exposing the reference's public names; ``key`` in c1..c5."""
+    return _BUILDERS[key](nd)
+
+
+def sample_coords(workload, n, seed=0):
+    """Synthetic uniform points in the workload's box: float32 array [d0, n] (SoA), deterministic per seed."""
+    rs = np.random.RandomState(seed)
+    rows = []
+    for lo, hi in workload.coord_ranges:
+        rows.append((lo + (hi - lo) * rs.rand(n)).astype(np.float32))
+    return np.stack(rows, axis=0)
+
+
+def bundle_eq_wrapper(workload):
+    """diff_eqs as BundleSolver1D would call it (reference solvers.py:1353-1361): funcs, t, theta[eq_param_index]."""
+    if workload.eq_param_index is None:
+        return workload.diff_eqs
+    n_funcs = len(workload.nets_spec) if workload.solver != "BundleSolver1D" else 2
+    idx = tuple(n_funcs + 1 + i for i in workload.eq_param_index)
+
+    def wrapped(*variables):
+        head = variables[:n_funcs + 1]
+        return workload.diff_eqs(*head, *(variables[i] for i in idx))
+
+    return wrapped
