@@ -1,0 +1,239 @@
+"""Condition re-parameterisations accepted by the fused path (reference neurodiffeq/conditions.py).
+
+Every ``parameterize`` is written once with plain arithmetic and ``.exp()`` style methods, so that it runs
+
+* on traced symbols -- the fused solvers call ``enforce(net, *coords)`` ONCE with symbolic coordinates; the network call
+  is recorded as a jet leaf (no ``torch.cat``, no forward pass) and the closed form becomes part of the residual
+  program that the CUDA kernels evaluate per point and differentiate exactly;
+* on eager tensors -- same signatures and values as the reference, for user code outside the solver.
+
+User-supplied boundary callables (``x_min_val=lambda y: torch.sin(np.pi*y)`` ...) are traced through
+``Sym.__torch_function__``.
+
+Implemented: NoCondition :205-222, IVP :225-267, BundleIVP :270-345, DirichletBVP :398-435,
+BundleDirichletBVP :348-395, DirichletBVP2D :438-509, IBVP1D Dirichlet-Dirichlet :661-681,
+DirichletBVPSpherical :887-956, InfDirichletBVPSpherical :960-1019.  The Neumann flavours of IBVP1D / DoubleEndedBVP1D
+evaluate the network at boundary points (conditions.py:685-712) -- a second forward pass at other coordinates, not yet
+in the kernels -- and raise NotImplementedError.
+"""
+import warnings
+
+import torch
+
+from . import symbolic as _sym
+
+
+def _exp(x):
+    return x.exp() if hasattr(x, "exp") else torch.exp(torch.as_tensor(x))
+
+
+def _abs(x):
+    return x.abs() if hasattr(x, "abs") else abs(x)
+
+
+class BaseCondition:
+    """Base class (reference conditions.py:10-75): ``enforce`` = network call + ``parameterize``."""
+
+    def __init__(self):
+        self.ith_unit = None
+
+    def parameterize(self, output_tensor, *input_tensors):
+        raise ValueError(f"Abstract {self.__class__.__name__} cannot be parameterized")
+
+    def _network_output(self, net, *coordinates):
+        if _sym.is_symbolic(*coordinates):
+            g = coordinates[0].g
+            in_coord = []
+            for c in coordinates:
+                if not isinstance(c, _sym.Sym) or c.op != "coord":
+                    raise NotImplementedError("fused enforce(): the network inputs must be the sampled coordinates")
+                in_coord.append(c.imm)
+            n = g.register_net(net, in_coord)
+            return g.net(n, self.ith_unit if self.ith_unit is not None else 0), n
+        out = net(torch.cat(coordinates, dim=1))
+        if self.ith_unit is not None:
+            out = out[:, self.ith_unit].view(-1, 1)
+        return out, None
+
+    def enforce(self, net, *coordinates):
+        out, _ = self._network_output(net, *coordinates)
+        return self.parameterize(out, *coordinates)
+
+    def set_impose_on(self, ith_unit):
+        warnings.warn(f"`{self.__class__.__name__}.set_impose_on` is deprecated and will be removed in the future",
+                      DeprecationWarning)
+        self.ith_unit = ith_unit
+
+
+class NoCondition(BaseCondition):
+    def parameterize(self, output_tensor, *input_tensors):
+        return output_tensor
+
+
+class _BundleConditionMixin:
+    """Bundle parameters are taken per point from ``thetas`` by index (reference conditions.py:78-135)."""
+
+    def __init__(self, bundle_param_lookup=None, allowed_params=None):
+        self.bundle_param_lookup = bundle_param_lookup or {}
+        if isinstance(allowed_params, str):
+            allowed_params = set(allowed_params)
+        if allowed_params:
+            illegal = set(self.bundle_param_lookup) - set(allowed_params)
+            if illegal:
+                raise ValueError(f"The following parameter(s) are not allowed in `bundle_parameters_lookup`: "
+                                 f"{illegal}.\nSupported parameter name(s) are: {allowed_params}.")
+
+    def _get_parameter(self, param_name, thetas, override_name=None):
+        if param_name in self.bundle_param_lookup:
+            return thetas[self.bundle_param_lookup[param_name]]
+        return getattr(self, override_name or param_name)
+
+
+def _ivp_form(out, t, t_0, u_0, u_0_prime):
+    decay = 1 - _exp(-t + t_0)
+    if u_0_prime is None:
+        return u_0 + decay * out
+    return u_0 + (t - t_0) * u_0_prime + (decay ** 2) * out
+
+
+class IVP(BaseCondition):
+    """u(t0)=u0 [and u'(t0)=u0']:  u = u0 + (1-e^{-(t-t0)}) N   /   u0 + (t-t0)u0' + (1-e^{-(t-t0)})^2 N."""
+
+    def __init__(self, t_0, u_0=None, u_0_prime=None, **legacy):
+        super().__init__()
+        if "x_0" in legacy:
+            u_0 = legacy.pop("x_0")
+        if "x_0_prime" in legacy:
+            u_0_prime = legacy.pop("x_0_prime")
+        if legacy:
+            raise TypeError(f"unexpected arguments {list(legacy)}")
+        self.t_0, self.u_0, self.u_0_prime = t_0, u_0, u_0_prime
+
+    def parameterize(self, output_tensor, t):
+        return _ivp_form(output_tensor, t, self.t_0, self.u_0, self.u_0_prime)
+
+
+class BundleIVP(BaseCondition, _BundleConditionMixin):
+    def __init__(self, t_0=None, u_0=None, u_0_prime=None, bundle_param_lookup=None, **legacy):
+        BaseCondition.__init__(self)
+        if "bundle_conditions" in legacy:
+            bundle_param_lookup = legacy.pop("bundle_conditions")
+        if legacy:
+            raise TypeError(f"unexpected arguments {list(legacy)}")
+        _BundleConditionMixin.__init__(self, bundle_param_lookup=bundle_param_lookup,
+                                       allowed_params=["t_0", "u_0", "u_0_prime"])
+        self.t_0, self.u_0, self.u_0_prime = t_0, u_0, u_0_prime
+
+    def parameterize(self, output_tensor, t, *theta):
+        return _ivp_form(output_tensor, t, self._get_parameter("t_0", theta), self._get_parameter("u_0", theta),
+                         self._get_parameter("u_0_prime", theta))
+
+
+def _two_point_form(out, t, t_0, u_0, t_1, u_1):
+    tt = (t - t_0) / (t_1 - t_0)
+    return u_0 * (1 - tt) + u_1 * tt + (1 - _exp((1 - tt) * tt)) * out
+
+
+class DirichletBVP(BaseCondition):
+    """u(t0)=u0, u(t1)=u1 (reference conditions.py:398-435)."""
+
+    def __init__(self, t_0, u_0, t_1, u_1):
+        super().__init__()
+        self.t_0, self.u_0, self.t_1, self.u_1 = t_0, u_0, t_1, u_1
+
+    def parameterize(self, output_tensor, t):
+        return _two_point_form(output_tensor, t, self.t_0, self.u_0, self.t_1, self.u_1)
+
+
+class BundleDirichletBVP(BaseCondition, _BundleConditionMixin):
+    def __init__(self, t_0=None, u_0=None, t_1=None, u_1=None, bundle_param_lookup=None):
+        BaseCondition.__init__(self)
+        _BundleConditionMixin.__init__(self, bundle_param_lookup=bundle_param_lookup,
+                                       allowed_params=["t_0", "u_0", "t_1", "u_1"])
+        self.t_0, self.u_0, self.t_1, self.u_1 = t_0, u_0, t_1, u_1
+
+    def parameterize(self, output_tensor, t, *theta):
+        return _two_point_form(output_tensor, t, *(self._get_parameter(k, theta) for k in ("t_0", "u_0", "t_1", "u_1")))
+
+
+class DirichletBVP2D(BaseCondition):
+    """Dirichlet data on the four sides of [x0,x1]x[y0,y1]: u = A(x,y) + x~(1-x~) y~(1-y~) N (conditions.py:438-509)."""
+
+    def __init__(self, x_min, x_min_val, x_max, x_max_val, y_min, y_min_val, y_max, y_max_val):
+        super().__init__()
+        self.x0, self.f0 = x_min, x_min_val
+        self.x1, self.f1 = x_max, x_max_val
+        self.y0, self.g0 = y_min, y_min_val
+        self.y1, self.g1 = y_max, y_max_val
+
+    def parameterize(self, output_tensor, x, y):
+        xt = (x - self.x0) / (self.x1 - self.x0)
+        yt = (y - self.y0) / (self.y1 - self.y0)
+        if _sym.is_symbolic(x):
+            x_lo, x_hi = x.g.const(self.x0), x.g.const(self.x1)
+        else:
+            x_lo, x_hi = torch.full_like(x, self.x0), torch.full_like(x, self.x1)
+
+        def minus_corners(g_side):  # subtract the linear interpolant of the corner values
+            return g_side(x) - ((1 - xt) * g_side(x_lo) + xt * g_side(x_hi))
+
+        a_xy = (1 - xt) * self.f0(y) + xt * self.f1(y) + (1 - yt) * minus_corners(self.g0) + yt * minus_corners(self.g1)
+        return a_xy + xt * (1 - xt) * yt * (1 - yt) * output_tensor
+
+
+class IBVP1D(BaseCondition):
+    """u(x,t0)=u0(x) with Dirichlet data g(t), h(t) at x0, x1 (reference conditions.py:512-712, DD branch)."""
+
+    def __init__(self, x_min, x_max, t_min, t_min_val, x_min_val=None, x_min_prime=None, x_max_val=None,
+                 x_max_prime=None):
+        super().__init__()
+        n_conditions = sum(c is not None for c in [x_min_val, x_min_prime, x_max_val, x_max_prime])
+        if n_conditions != 2 or (x_min_val and x_min_prime) or (x_max_val and x_max_prime):
+            raise NotImplementedError("Sorry, this boundary condition is not implemented.")
+        self.x_min, self.x_min_val, self.x_min_prime = x_min, x_min_val, x_min_prime
+        self.x_max, self.x_max_val, self.x_max_prime = x_max, x_max_val, x_max_prime
+        self.t_min, self.t_min_val = t_min, t_min_val
+
+    def enforce(self, net, x, t):
+        if not (self.x_min_val and self.x_max_val):
+            raise NotImplementedError(
+                "IBVP1D with Neumann data evaluates the network at the boundary (reference conditions.py:685-712); "
+                "only the Dirichlet-Dirichlet form is implemented in the fused kernels")
+        out, _ = self._network_output(net, x, t)
+        return self.parameterize(out, x, t)
+
+    def parameterize(self, u, x, t, *additional_tensors):
+        t0 = t.g.const(self.t_min) if _sym.is_symbolic(t) else torch.full_like(t, self.t_min)
+        xt = (x - self.x_min) / (self.x_max - self.x_min)
+        a_xt = self.t_min_val(x) + xt * (self.x_max_val(t) - self.x_max_val(t0)) \
+            + (1 - xt) * (self.x_min_val(t) - self.x_min_val(t0))
+        return a_xt + xt * (1 - xt) * (1 - _exp(-(t - self.t_min))) * u
+
+
+class DirichletBVPSpherical(BaseCondition):
+    """u(r0,.)=f, u(r1,.)=g on spherical shells (reference conditions.py:887-956)."""
+
+    def __init__(self, r_0, f, r_1=None, g=None):
+        super().__init__()
+        if (r_1 is None) ^ (g is None):
+            raise ValueError(f"r_1 and g must be both/neither set to None; got r_1={r_1}, g={g}")
+        self.r_0, self.r_1, self.f, self.g = r_0, r_1, f, g
+
+    def parameterize(self, output_tensor, r, theta, phi):
+        if self.r_1 is None:
+            return (1 - _exp(-_abs(r - self.r_0))) * output_tensor + self.f(theta, phi)
+        rt = (r - self.r_0) / (self.r_1 - self.r_0)
+        return self.f(theta, phi) * (1 - rt) + self.g(theta, phi) * rt + (1. - _exp((1 - rt) * rt)) * output_tensor
+
+
+class InfDirichletBVPSpherical(BaseCondition):
+    """u(r0,.)=f and u(r->inf,.)=g with decay order ``order`` (reference conditions.py:960-1019)."""
+
+    def __init__(self, r_0, f, g, order=1):
+        super().__init__()
+        self.r_0, self.f, self.g, self.order = r_0, f, g, order
+
+    def parameterize(self, output_tensor, r, theta, phi):
+        dr = r - self.r_0
+        decay, rise = _exp(-self.order * dr), dr.tanh()
+        return self.f(theta, phi) * decay + self.g(theta, phi) * rise + decay * rise * output_tensor

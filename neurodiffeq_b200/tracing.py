@@ -1,0 +1,160 @@
+"""Trace (conditions, diff_eqs) once -> the static description the CUDA engine needs.
+
+This replaces, for the fused path, everything the reference does per batch in Python between ``_generate_batch`` and
+``loss.backward()`` (solvers.py:369-395): the closed forms are extracted ONCE at solver construction:
+
+* which networks are evaluated, fed by which coordinates (``BaseCondition.enforce``, conditions.py:41-57),
+* which derivative jets of every raw network output the residuals need (-> :class:`ChannelScheme`),
+* an *eval* program   coords, jets -> u_k (re-parameterised functions), r_e (residuals),
+* a *train* program   coords, jets -> r_e and the seeds  dL/d(jet)  for  L = mean(r^2)  (solvers.py:218) or for an
+  externally supplied  dL/dr  (custom ``loss_fn``), obtained by symbolic reverse differentiation.
+"""
+import numpy as np
+import torch.nn as nn
+
+from . import symbolic as S
+from .networks import SinActv
+
+ACT_TANH, ACT_SIN = 0, 1
+
+
+class NetDescription:
+    """Static view of one distinct network: widths, activation, the nn.Linear modules, input coordinates."""
+
+    def __init__(self, module, in_coord):
+        self.module = module
+        self.in_coord = tuple(in_coord)
+        seq = getattr(module, "NN", module)
+        if not isinstance(seq, nn.Sequential):
+            raise NotImplementedError(
+                f"fused path supports FCNN-style networks (nn.Sequential of Linear/activation); got "
+                f"{type(module).__name__}.  (Resnet / MonomialNN / custom modules: not implemented)")
+        mods = list(seq)
+        self.linears, acts = [], []
+        for k, m in enumerate(mods):
+            if k % 2 == 0:
+                if not isinstance(m, nn.Linear):
+                    raise NotImplementedError(f"expected nn.Linear at position {k} of the network, got {type(m).__name__}")
+                if m.bias is None:
+                    raise NotImplementedError("Linear layers without bias are not supported by the fused kernels")
+                self.linears.append(m)
+            else:
+                acts.append(m)
+        if len(mods) % 2 == 0 or len(self.linears) < 2:
+            raise NotImplementedError("network must be Linear, actv, ..., Linear with at least one hidden layer")
+        kinds = set()
+        for a in acts:
+            if isinstance(a, nn.Tanh):
+                kinds.add(ACT_TANH)
+            elif isinstance(a, SinActv) or type(a).__name__ == "SinActv":
+                kinds.add(ACT_SIN)
+            else:
+                raise NotImplementedError(f"activation {type(a).__name__} has no jet rule in the fused kernels "
+                                          f"(implemented: nn.Tanh, SinActv)")
+        if len(kinds) != 1:
+            raise NotImplementedError("all hidden activations of one network must be the same")
+        self.act = kinds.pop()
+        self.widths = [self.linears[0].in_features] + [m.out_features for m in self.linears]
+        for a, b in zip(self.linears[:-1], self.linears[1:]):
+            if a.out_features != b.in_features:
+                raise ValueError("inconsistent layer widths")
+        if self.widths[0] != len(self.in_coord):
+            raise ValueError(f"network expects {self.widths[0]} inputs but the condition passes "
+                             f"{len(self.in_coord)} coordinates")
+
+    @property
+    def n_out(self):
+        return self.widths[-1]
+
+    def parameters(self):
+        out = []
+        for m in self.linears:
+            out += [m.weight, m.bias]
+        return out
+
+
+class TracedProblem:
+    def __init__(self, nets, conditions, diff_eqs, n_coords, coords_for_condition=None):
+        """``nets[k]`` / ``conditions[k]`` as in the reference solver; ``diff_eqs(*funcs, *coords)``.
+        ``coords_for_condition(k, cond, coords) -> tuple`` lets SolverSpherical trim coordinates
+        (reference solvers.py:894-916)."""
+        g = S.Graph()
+        self.graph = g
+        self.n_coords = n_coords
+        coords = [g.coord(i) for i in range(n_coords)]
+        funcs = []
+        for k, (net, cond) in enumerate(zip(nets, conditions)):
+            cc = coords if coords_for_condition is None else coords_for_condition(k, cond, coords)
+            funcs.append(g.lift(cond.enforce(net, *cc)))
+        res = diff_eqs(*funcs, *coords)
+        if isinstance(res, S.Sym) or not hasattr(res, "__len__"):
+            res = [res]
+        residuals = [g.lift(r) for r in res]
+        self.n_funcs, self.n_eq = len(funcs), len(residuals)
+        self.nets = [NetDescription(m, ic) for m, ic in g.nets]
+        if not self.nets:
+            raise ValueError("no network is evaluated by the conditions")
+
+        # --- which jets are needed -> channel scheme ------------------------------------------------------------------
+        leaves = [n for n in S.topo_order(funcs + residuals) if n.op == "net"]
+        for n in leaves:
+            net_idx, o, _ = n.imm
+            if o >= self.nets[net_idx].n_out:
+                raise ValueError(f"condition selects output unit {o} of a network with "
+                                 f"{self.nets[net_idx].n_out} outputs")
+        self.scheme = S.ChannelScheme(n_coords, [n.imm[2] for n in leaves])
+        C = self.scheme.n_channels
+        self.yrow0 = []
+        row = 0
+        for nd in self.nets:
+            self.yrow0.append(row)
+            row += nd.n_out * C
+        self.n_yrows = row
+
+        mapping = {}
+        for n in leaves:
+            net_idx, o, alpha = n.imm
+            if len(alpha) == 2 and alpha[0] != alpha[1]:
+                i, j = alpha
+                v = [0.0] * n_coords
+                v[i] = v[j] = 1.0
+                cd = self.scheme.second_channel_of_dir(v)
+                mapping[n] = g.mul(0.5, g.sub(g.sub(g.ych(net_idx, o, cd),
+                                                    g.ych(net_idx, o, self.scheme.channel_of((i, i)))),
+                                              g.ych(net_idx, o, self.scheme.channel_of((j, j)))))
+            else:
+                mapping[n] = g.ych(net_idx, o, self.scheme.channel_of(alpha))
+        resolved = S.substitute(funcs + residuals, mapping)
+        self.funcs, self.residuals = resolved[:self.n_funcs], resolved[self.n_funcs:]
+
+        yrow = lambda net_idx, o, c: self.yrow0[net_idx] + o * C + c  # noqa: E731
+        self._yrow = yrow
+        # --- programs ---------------------------------------------------------------------------------------------------
+        self.prog_eval = S.lower([(S.OP_ST_U, k, f) for k, f in enumerate(self.funcs)]
+                                 + [(S.OP_ST_R, e, r) for e, r in enumerate(self.residuals)], yrow)
+        self.prog_train = self._train_program(external_rbar=False)
+        self._prog_train_ext = None
+
+    def _train_program(self, external_rbar):
+        g = self.graph
+        if external_rbar:
+            cots = [(r, g.rbar(e)) for e, r in enumerate(self.residuals)]
+        else:  # L = scale/2 * sum r^2 with scale = 2/(N n_eq)  ->  dL/dr = scale * r
+            cots = [(r, g.mul(g.param(S.PARAM_LOSS_SCALE), r)) for r in self.residuals]
+        adj = S.reverse_gradients(cots)
+        by_row = {self._yrow(*leaf.imm): expr for leaf, expr in adj.items()}
+        outs = [(S.OP_ST_R, e, r) for e, r in enumerate(self.residuals)]
+        zero = g.const(0.0)
+        for row in range(self.n_yrows):
+            outs.append((S.OP_ST_SEED, row, by_row.get(row, zero)))
+        return S.lower(outs, self._yrow)
+
+    @property
+    def prog_train_ext(self):
+        if self._prog_train_ext is None:
+            self._prog_train_ext = self._train_program(external_rbar=True)
+        return self._prog_train_ext
+
+    def direction_matrix(self):
+        """[n1, n_coords] float32: direction vectors of the first-order channels."""
+        return np.asarray(self.scheme.dirs, dtype=np.float32).reshape(self.scheme.n1, self.n_coords)

@@ -1,0 +1,94 @@
+"""Host logic: tracing the reference-style problem definitions -> programs; algebra of the kernels (numpy mirror)
+against golden vectors produced by the unmodified reference."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import workloads
+from conftest import load_golden
+from oracle import jet_numpy
+
+
+def product_namespace():
+    from neurodiffeq_b200 import diff
+    from neurodiffeq_b200 import operators as ops
+    from neurodiffeq_b200.networks import FCNN, SinActv
+    from neurodiffeq_b200 import conditions as c
+    return types.SimpleNamespace(
+        diff=diff, FCNN=FCNN, SinActv=SinActv, IVP=c.IVP, BundleIVP=c.BundleIVP, DirichletBVP2D=c.DirichletBVP2D,
+        IBVP1D=c.IBVP1D, DirichletBVPSpherical=c.DirichletBVPSpherical, NoCondition=c.NoCondition,
+        spherical_laplacian=ops.spherical_laplacian, laplacian=ops.laplacian, grad=ops.grad, div=ops.div,
+        curl=ops.curl)
+
+
+def trace(key):
+    from neurodiffeq_b200.tracing import TracedProblem
+    wl = workloads.build(product_namespace(), key)
+    nets, conds = wl.make_nets(), wl.make_conditions()
+    tp = TracedProblem(nets, conds, workloads.bundle_eq_wrapper(wl), len(wl.coord_names))
+    return wl, nets, conds, tp
+
+
+EXPECTED_CHANNELS = {"c1": (1, 0), "c2": (2, 2), "c3": (2, 1), "c4": (3, 3), "c5": (1, 0)}
+
+
+@pytest.mark.parametrize("key", workloads.NAMES)
+def test_traced_problem_matches_reference_golden(key):
+    wl, nets, conds, tp = trace(key)
+    assert (tp.scheme.n1, tp.scheme.n2) == EXPECTED_CHANNELS[key]
+    gold = load_golden(wl.name)
+    # golden params are in state_dict order over the distinct nets = [W0,b0,W1,b1,...] per net
+    per_net, it = [], iter(gold["params"])
+    for nd in tp.nets:
+        per_net.append([next(it) for _ in range(2 * len(nd.linears))])
+    out = jet_numpy.run_traced(tp, per_net, gold["coords"])
+    rms = np.sqrt((gold["residual"] ** 2).mean())
+    np.testing.assert_allclose(out["u"], gold["u"], rtol=1e-10, atol=1e-12)
+    assert np.abs(out["residual"] - gold["residual"]).max() <= 1e-9 * rms
+    assert abs(out["loss"] - gold["loss"]) <= 1e-10 * gold["loss"]
+    gn = np.sqrt(sum((g ** 2).sum() for g in gold["grads"]))
+    dn = np.sqrt(sum(((g - h.reshape(g.shape)) ** 2).sum() for g, h in zip(gold["grads"], out["grads"])))
+    assert dn <= 1e-9 * gn
+    print(key, "eval prog", len(tp.prog_eval), "slots", tp.prog_eval.n_slots, "| train prog", len(tp.prog_train),
+          "slots", tp.prog_train.n_slots)
+
+
+def test_mixed_partials_by_polarisation():
+    """u_xy is carried as (D_{x+y}^2 - D_x^2 - D_y^2)/2; checked against autograd on a random FCNN."""
+    from neurodiffeq_b200 import diff
+    from neurodiffeq_b200.networks import FCNN
+    from neurodiffeq_b200.conditions import NoCondition
+    from neurodiffeq_b200.tracing import TracedProblem
+    torch.manual_seed(3)
+    net = FCNN(2, 1, hidden_units=(16, 16)).double()
+    eq = lambda u, x, y: [diff(diff(u, x), y) + diff(u, x, order=2) * y - diff(u, y)]  # noqa: E731
+    tp = TracedProblem([net], [NoCondition()], eq, 2)
+    assert tp.scheme.n2 == 3 and tp.scheme.n1 == 3
+    coords = np.random.RandomState(0).rand(2, 64)
+    params = [[p.detach().numpy() for p in net.parameters()]]
+    out = jet_numpy.run_traced(tp, params, coords)
+    x, y = (torch.tensor(c).reshape(-1, 1).requires_grad_(True) for c in coords)
+    u = net(torch.cat([x, y], 1))
+    r = eq(u, x, y)[0]
+    loss = (r ** 2).mean()
+    loss.backward()
+    np.testing.assert_allclose(out["residual"][0], r.detach().numpy()[:, 0], rtol=1e-9, atol=1e-11)
+    for g, p in zip(out["grads"], net.parameters()):
+        ref = np.zeros(p.shape) if p.grad is None else p.grad.numpy()  # output bias: no gradient at all
+        np.testing.assert_allclose(g.reshape(p.shape), ref, rtol=1e-8, atol=1e-11)
+
+
+def test_unused_coordinate_gives_zero_and_order3_raises():
+    from neurodiffeq_b200 import diff
+    from neurodiffeq_b200.networks import FCNN
+    from neurodiffeq_b200.conditions import NoCondition
+    from neurodiffeq_b200.tracing import TracedProblem
+    net = FCNN(1, 1, hidden_units=(8,))
+    tp = TracedProblem([net], [NoCondition()], lambda u, t: [diff(u, t) + diff(t * t, t) + diff(3.0 * t, t, order=2)], 1)
+    assert (tp.scheme.n1, tp.scheme.n2) == (1, 0)
+    with pytest.raises(NotImplementedError):
+        TracedProblem([net], [NoCondition()], lambda u, t: [diff(u, t, order=3)], 1)
+    with pytest.raises(TypeError):
+        TracedProblem([net], [NoCondition()], lambda u, t: [u if u > 0 else -u], 1)
