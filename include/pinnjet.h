@@ -1,0 +1,120 @@
+/*
+ * pinnjet.h -- C ABI of libpinnjet.so: the B200-native PINN residual + parameter-gradient engine.
+ *
+ * The reference (NeuroDiffGym/neurodiffeq @ 9f6d6e3) has NO FFI: its hot path is the Python closure at
+ * neurodiffeq/solvers.py:369-395 orchestrating ~500 ATen calls per batch.  This header is the boundary a maintainer
+ * would bind instead (ctypes stub: INTEGRATION.md).  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "device" is a CUDA device pointer owned by the CALLER (PyTorch);
+ *   - the library allocates nothing persistent and keeps no pointer after a call returns;
+ *   - all work is enqueued on the given stream (pass torch.cuda.current_stream().cuda_stream), no host sync inside,
+ *     no allocation: every call is CUDA-graph capturable;
+ *   - return value 0 = success, negative = error; message via pj_last_error() (thread-local), never throws/exits.
+ *
+ * Data layout
+ *   coords      : SoA, n_coords device pointers to float[N]  (what generators.py hands out as (N,1) columns)
+ *   theta       : flat float32, every nn.Linear in torch layout W[out][in] then b[out], offsets in PjNet
+ *                 (= the live nn.Parameter storage; reference networks.py:62-66)
+ *   grad_theta  : same layout; pj_backward ACCUMULATES (+=) like loss.backward() (solvers.py:360-362, 393)
+ *   u_out       : float[n_funcs][N]   re-parameterised functions  (conditions.py:41-57)
+ *   resid_out   : float[n_eq][N]      residuals of diff_eqs       (solvers.py:380-381, transposed: SoA)
+ *   program     : int32[len][4] bytecode produced by neurodiffeq_b200/symbolic.py (op,dst,a,b)
+ */
+#ifndef PINNJET_H
+#define PINNJET_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PJ_ABI_VERSION 1
+#define PJ_MAX_NETS 4
+#define PJ_MAX_LINEAR 8   /* nn.Linear layers per network (hidden layers + 1) */
+#define PJ_MAX_COORDS 8
+#define PJ_MAX_DIRS 4     /* first-order jet directions */
+#define PJ_MAX_WIDTH 128  /* hidden width */
+#define PJ_ACT_TANH 0
+#define PJ_ACT_SIN 1
+
+/* One FCNN (reference networks.py:6-70): Linear, actv, ..., Linear. */
+typedef struct PjNet {
+    int32_t n_in;                       /* network inputs                                                    */
+    int32_t in_coord[PJ_MAX_COORDS];    /* input i is coordinate in_coord[i]  (conditions.py:52 torch.cat)    */
+    int32_t n_linear;                   /* number of nn.Linear layers (>= 2)                                  */
+    int32_t width[PJ_MAX_LINEAR + 1];   /* width[0]=n_in, width[l]=out_features of Linear l-1                 */
+    int32_t act;                        /* PJ_ACT_*                                                           */
+    int32_t yrow0;                      /* first row of this net in the jet table: row = yrow0 + o*C + c      */
+    int64_t w_off[PJ_MAX_LINEAR];       /* float offset of W_l (torch layout [out][in]) in theta / grad_theta */
+    int64_t b_off[PJ_MAX_LINEAR];       /* float offset of b_l                                                */
+} PjNet;
+
+/* Static problem description extracted once by the host (neurodiffeq_b200/tracing.py). */
+typedef struct PjSpec {
+    int32_t abi_version;                /* PJ_ABI_VERSION                                                     */
+    int32_t n_coords;                   /* number of sampled coordinates (d0)                                 */
+    int32_t n_nets;                     /* distinct networks                                                  */
+    int32_t n1, n2;                     /* jet channels: value | n1 directional firsts | n2 pure seconds      */
+    float dir[PJ_MAX_DIRS][PJ_MAX_COORDS]; /* direction vectors of the first-order channels (coordinate space) */
+    int32_t n_funcs, n_eq;              /* outputs of the eval program                                        */
+    int32_t n_yrows;                    /* rows of the jet table = sum_n n_out(n) * C                         */
+    int32_t n_slots;                    /* value-file size the programs need                                  */
+    int64_t n_theta;                    /* floats in theta                                                    */
+    PjNet net[PJ_MAX_NETS];
+} PjSpec;
+
+/* Sizes the caller needs to allocate buffers (all bytes; workspace contents are opaque). */
+typedef struct PjSizes {
+    int64_t pack_bytes;                 /* packed/transposed weight copy written by pj_pack                   */
+    int64_t workspace_bytes;            /* z-jets + seeds + per-CTA gradient partials for N points            */
+    int32_t tile_points;                /* collocation points per tile                                        */
+    int32_t grid;                       /* persistent CTAs launched                                           */
+    int32_t smem_forward, smem_backward;/* dynamic shared memory per CTA                                      */
+    int32_t launches_forward, launches_backward;
+} PjSizes;
+
+int pj_abi_version(void);
+const char* pj_last_error(void);
+
+/* Buffer sizes for N points on the current device. */
+int pj_sizes(const PjSpec* spec, int64_t n_points, PjSizes* out);
+
+/* Diagnostics: the tiling plan as int64 numbers (tests compare workspace contents with the CPU mirror).
+ * out[0..18] = T,P,Q,C,RS,n_tiles,grid,hmax,n_stage_fwd,n_stage_bwd,resident_fwd,resident_bwd,zj_tile_floats,
+ *              ws_zj,ws_seed,ws_gpart,ws_bytes,smem_fwd,smem_bwd; then hp[net][0..8] and zj_off[net][0..7] per net. */
+int pj_plan_info(const PjSpec* spec, int64_t n_points, int64_t* out, int32_t n_out);
+
+/* Re-layout the live parameters for the kernels (K-major + padded copies).  Call after every optimizer step.
+ * Replaces nothing in the reference (its weights are read in place by aten::addmm); cost: one tiny launch. */
+int pj_pack(const PjSpec* spec, const float* theta /*device*/, float* theta_pack /*device*/, void* stream);
+
+/* Inference / validation: u and residual at N points, optional sum of squared residuals.
+ * Replaces  funcs = cond.enforce(net, *coords); residuals = diff_eqs(*funcs, *coords)
+ *           (solvers.py:373-381, get_residuals :606-646, BaseSolution.__call__ :682-720).
+ * u_out / resid_out / sumsq_out may be NULL.  *sumsq_out += sum over points and equations of r^2.            */
+int pj_forward(const PjSpec* spec, const int32_t* prog_eval /*device*/, int32_t prog_len,
+               const float* const* coords /*host array of device ptrs*/, int64_t n_points,
+               const float* theta_pack /*device*/, float* u_out, float* resid_out, float* sumsq_out,
+               void* workspace /*device*/, size_t workspace_bytes, void* stream);
+
+/* Training forward: residual program + seeds dL/d(jet) + z-jets into the workspace for pj_backward.
+ * loss = loss_scale/2 * sum r^2 with loss_scale = 2/(N_global*n_eq)  (solvers.py:218: (r**2).mean()).
+ * If rbar != NULL it is float[n_eq][N] = dL/dr supplied by the caller (custom loss_fn, solvers.py:216-226) and the
+ * program must be the external-cotangent variant.  resid_out may be NULL.  *sumsq_out += sum r^2.             */
+int pj_forward_train(const PjSpec* spec, const int32_t* prog_train /*device*/, int32_t prog_len,
+                     const float* const* coords, int64_t n_points, const float* theta_pack,
+                     float loss_scale, const float* rbar, float* resid_out, float* sumsq_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Reverse pass: grad_theta += dL/dtheta  (replaces loss.backward(), solvers.py:393).
+ * Must follow pj_forward_train on the same workspace / points / theta_pack.                                    */
+int pj_backward(const PjSpec* spec, const float* const* coords, int64_t n_points, const float* theta_pack,
+                float* grad_theta /*device, accumulated*/, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINNJET_H */

@@ -1,0 +1,393 @@
+// pinnjet_api.cu -- C ABI of libpinnjet.so (include/pinnjet.h): planning, the pack kernel and the launch wrappers.
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+
+#include "pinnjet_common.cuh"
+
+namespace pj {
+
+// per-scheme launchers, defined in pinnjet_inst.cu (one translation unit per jet-channel scheme)
+#define PJ_DECL(N1, N2)                                                                  \
+    cudaError_t launch_k1_##N1##_##N2(const K1Args& a, int grid, int smem, cudaStream_t s); \
+    cudaError_t launch_k2_##N1##_##N2(const K2Args& a, int grid, int smem, cudaStream_t s);
+PJ_DECL(1, 0)
+PJ_DECL(1, 1)
+PJ_DECL(2, 0)
+PJ_DECL(2, 1)
+PJ_DECL(2, 2)
+PJ_DECL(3, 0)
+PJ_DECL(3, 3)
+#undef PJ_DECL
+cudaError_t launch_reduce(const float* gpart, int n_parts, long long n_theta, float* grad, cudaStream_t s);
+cudaError_t launch_loss_finalize(const float* part, int n_parts, float* out, cudaStream_t s);
+
+typedef cudaError_t (*K1Launch)(const K1Args&, int, int, cudaStream_t);
+typedef cudaError_t (*K2Launch)(const K2Args&, int, int, cudaStream_t);
+struct SchemeEntry {
+    int n1, n2;
+    K1Launch k1;
+    K2Launch k2;
+};
+static const SchemeEntry kSchemes[] = {
+    {1, 0, launch_k1_1_0, launch_k2_1_0}, {1, 1, launch_k1_1_1, launch_k2_1_1}, {2, 0, launch_k1_2_0, launch_k2_2_0},
+    {2, 1, launch_k1_2_1, launch_k2_2_1}, {2, 2, launch_k1_2_2, launch_k2_2_2}, {3, 0, launch_k1_3_0, launch_k2_3_0},
+    {3, 3, launch_k1_3_3, launch_k2_3_3},
+};
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static const SchemeEntry* find_scheme(int n1, int n2) {
+    for (const auto& e : kSchemes)
+        if (e.n1 == n1 && e.n2 == n2) return &e;
+    return nullptr;
+}
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static long long round_up_ll(long long v, long long m) { return (v + m - 1) / m * m; }
+
+constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA on sm_100
+constexpr int LOSS_PART_BYTES = 4096;
+constexpr int PROG_MAX = 1024;
+
+// Everything the kernels need to agree on.  prog_len only moves the end of the K1 shared-memory image.
+static int make_plan(const PjSpec& sp, long long N, int prog_len, Plan& pl) {
+    memset(&pl, 0, sizeof(pl));
+    if (sp.abi_version != PJ_ABI_VERSION) return fail(-1, "PjSpec.abi_version %d != %d", sp.abi_version, PJ_ABI_VERSION);
+    if (sp.n_nets < 1 || sp.n_nets > PJ_MAX_NETS) return fail(-1, "n_nets=%d out of range", sp.n_nets);
+    if (sp.n_coords < 1 || sp.n_coords > PJ_MAX_COORDS) return fail(-1, "n_coords=%d out of range", sp.n_coords);
+    if (!find_scheme(sp.n1, sp.n2))
+        return fail(-2, "jet channel scheme (n1=%d, n2=%d) has no compiled kernel", sp.n1, sp.n2);
+    if (N < 1) return fail(-1, "n_points must be positive");
+    if (prog_len > PROG_MAX) return fail(-2, "residual program too long (%d > %d instructions)", prog_len, PROG_MAX);
+    if (sp.n_slots < 1 || sp.n_slots > 64) return fail(-2, "n_slots=%d out of range (1..64)", sp.n_slots);
+    const int C = 1 + sp.n1 + sp.n2;
+    pl.C = C;
+    if (C <= 2) { pl.P = 4; pl.Q = 4; } else { pl.P = 2; pl.Q = 4; }
+    int hmax = 32, yrows = 0;
+    for (int n = 0; n < sp.n_nets; ++n) {
+        const PjNet& net = sp.net[n];
+        if (net.n_linear < 2 || net.n_linear > PJ_MAX_LINEAR) return fail(-1, "net %d: n_linear=%d out of range", n, net.n_linear);
+        if (net.n_in < 1 || net.n_in > PJ_MAX_COORDS || net.width[0] != net.n_in) return fail(-1, "net %d: bad n_in", n);
+        const int n_out = net.width[net.n_linear];
+        if (n_out < 1 || n_out > PJ_MAX_NETS) return fail(-2, "net %d: %d output units (max %d)", n, n_out, PJ_MAX_NETS);
+        if (net.act != PJ_ACT_TANH && net.act != PJ_ACT_SIN) return fail(-2, "net %d: unknown activation", n);
+        if (net.yrow0 != yrows) return fail(-1, "net %d: yrow0 must be %d", n, yrows);
+        yrows += n_out * C;
+        pl.hp[n][0] = net.n_in;
+        pl.hp[n][net.n_linear] = n_out;
+        for (int i = 0; i < net.n_in; ++i)
+            if (net.in_coord[i] < 0 || net.in_coord[i] >= sp.n_coords) return fail(-1, "net %d: bad in_coord", n);
+        for (int h = 1; h < net.n_linear; ++h) {
+            if (net.width[h] < 1 || net.width[h] > PJ_MAX_WIDTH)
+                return fail(-2, "net %d: hidden width %d not in 1..%d", n, net.width[h], PJ_MAX_WIDTH);
+            pl.hp[n][h] = round_up(net.width[h], 32);
+            if (pl.hp[n][h] > hmax) hmax = pl.hp[n][h];
+        }
+    }
+    if (yrows != sp.n_yrows) return fail(-1, "n_yrows=%d but the nets need %d", sp.n_yrows, yrows);
+    if (yrows > 32) return fail(-2, "jet table has %d rows (max 32)", yrows);
+    if (hmax > 64) hmax = 128; else if (hmax > 32) hmax = 64;
+    pl.hmax = hmax;
+    pl.T = NT_COMPUTE * pl.P * pl.Q / hmax;
+    if ((pl.T / pl.P) % 8 != 0 || pl.T > EPI_BATCH) return fail(-3, "internal: tile %d unsupported", pl.T);
+    pl.RS = C * pl.T + ROW_PAD;
+    pl.n_tiles = (int)((N + pl.T - 1) / pl.T);
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return fail(-4, "cannot query the CUDA device");
+    pl.grid = pl.n_tiles < sms ? pl.n_tiles : sms;
+    if (pl.grid > LOSS_PART_BYTES / 4) pl.grid = LOSS_PART_BYTES / 4;
+
+    // ---- packed parameters ----
+    int off = 0;
+    for (int n = 0; n < sp.n_nets; ++n) {
+        const PjNet& net = sp.net[n];
+        const int L = net.n_linear - 1, n_out = net.width[net.n_linear];
+        pl.s_wt0[n] = off; off += round_up(net.n_in * pl.hp[n][1], 4);
+        for (int l = 0; l < L; ++l) { pl.s_b[n][l] = off; off += pl.hp[n][l + 1]; }
+        pl.s_wlt[n] = off; off += round_up(pl.hp[n][L] * n_out, 4);
+        pl.s_wlo[n] = off; off += round_up(pl.hp[n][L] * n_out, 4);
+        pl.s_bout[n] = off; off += 4;
+    }
+    pl.small_floats = off;
+    long long big = off;
+    pl.chunks_fwd = pl.chunks_bwd = 0;
+    for (int n = 0; n < sp.n_nets; ++n) {
+        const int L = sp.net[n].n_linear - 1;
+        for (int l = 1; l < L; ++l) {
+            const int hi = pl.hp[n][l], ho = pl.hp[n][l + 1];
+            pl.b_wt[n][l] = big; big += (long long)hi * ho;
+            pl.b_wo[n][l] = big; big += (long long)hi * ho;
+            pl.chunks_fwd += (hi + CHUNK_FLOATS / ho - 1) / (CHUNK_FLOATS / ho);
+            pl.chunks_bwd += (ho + CHUNK_FLOATS / hi - 1) / (CHUNK_FLOATS / hi);
+        }
+    }
+    pl.pack_floats = big;
+
+    // ---- shared-memory gradient accumulators ----
+    off = 0;
+    for (int n = 0; n < sp.n_nets; ++n) {
+        const PjNet& net = sp.net[n];
+        const int L = net.n_linear - 1, n_out = net.width[net.n_linear];
+        pl.g_w0[n] = off; off += pl.hp[n][1] * net.n_in;
+        for (int l = 0; l < L; ++l) { pl.g_b[n][l] = off; off += pl.hp[n][l + 1]; }
+        pl.g_wl[n] = off; off += n_out * pl.hp[n][L];
+        pl.g_bout[n] = off; off += 4;
+    }
+    pl.sgrad_floats = off;
+
+    // ---- workspace ----
+    long long zt = 0;
+    for (int n = 0; n < sp.n_nets; ++n)
+        for (int h = 1; h < sp.net[n].n_linear; ++h) { pl.zj_off[n][h] = (int)zt; zt += (long long)pl.hp[n][h] * pl.RS; }
+    pl.zj_tile_floats = zt;
+    pl.ws_loss = 0;
+    pl.ws_zj = LOSS_PART_BYTES;
+    pl.ws_seed = round_up_ll(pl.ws_zj + 4ll * zt * pl.n_tiles, 256);
+    pl.ws_gpart = round_up_ll(pl.ws_seed + 4ll * sp.n_yrows * pl.T * pl.n_tiles, 256);
+    pl.ws_bytes = round_up_ll(pl.ws_gpart + 4ll * sp.n_theta * pl.grid, 256);
+
+    // ---- shared memory images ----
+    const int jet_bytes = hmax * pl.RS * 4;
+    const int small_bytes = round_up(pl.small_floats * 4, 128);
+    const int misc_bytes = 256;
+    {   // K1: act | ring | small | ycache | slots | misc | prog
+        const int fixed = jet_bytes + small_bytes + sp.n_yrows * EPI_BATCH * 4 + sp.n_slots * EPI_BATCH * 4 + misc_bytes +
+                          prog_len * 16;
+        int ns = (SMEM_LIMIT - fixed) / (CHUNK_FLOATS * 4);
+        if (ns > MAX_STAGES) ns = MAX_STAGES;
+        if (ns > pl.chunks_fwd) ns = pl.chunks_fwd;
+        if (pl.chunks_fwd > 0 && ns < 2 && ns < pl.chunks_fwd) return fail(-2, "forward kernel does not fit in shared memory");
+        if (ns < 1) ns = 1;
+        pl.n_stage = ns;   // forward value; the backward value is stored in resident_bwd's companion below
+        pl.resident_fwd = ns >= pl.chunks_fwd;
+        int o = 0;
+        pl.k1_act = o; o += jet_bytes;
+        pl.k1_ring = o; o += ns * CHUNK_FLOATS * 4;
+        pl.k1_small = o; o += small_bytes;
+        pl.k1_ycache = o; o += sp.n_yrows * EPI_BATCH * 4;
+        pl.k1_slots = o; o += sp.n_slots * EPI_BATCH * 4;
+        pl.k1_misc = o; o += misc_bytes;
+        pl.k1_prog = o; o += prog_len * 16;
+        pl.k1_bytes = o;
+    }
+    {   // K2: G | G2 | Zb | ring | small | ybar | sgrad | misc
+        const int ybar_bytes = round_up(PJ_MAX_NETS * C * pl.T * 4, 128);
+        const int sgrad_bytes = round_up(pl.sgrad_floats * 4, 128);
+        const int fixed = 3 * jet_bytes + small_bytes + ybar_bytes + sgrad_bytes + misc_bytes;
+        int ns = (SMEM_LIMIT - fixed) / (CHUNK_FLOATS * 4);
+        if (ns > MAX_STAGES) ns = MAX_STAGES;
+        if (ns > pl.chunks_bwd) ns = pl.chunks_bwd;
+        if (pl.chunks_bwd > 0 && ns < 2 && ns < pl.chunks_bwd) return fail(-2, "backward kernel does not fit in shared memory");
+        if (ns < 1) ns = 1;
+        pl.resident_bwd = ns >= pl.chunks_bwd ? 1 : 0;
+        pl.chunks_bwd = pl.chunks_bwd;   // (kept)
+        int o = 0;
+        pl.k2_g0 = o; o += jet_bytes;
+        pl.k2_g1 = o; o += jet_bytes;
+        pl.k2_zb = o; o += jet_bytes;
+        pl.k2_ring = o; o += ns * CHUNK_FLOATS * 4;
+        pl.k2_small = o; o += small_bytes;
+        pl.k2_ybar = o; o += ybar_bytes;
+        pl.k2_sgrad = o; o += sgrad_bytes;
+        pl.k2_misc = o; o += misc_bytes;
+        pl.k2_bytes = o;
+        pl.n_stage_bwd = ns;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K0: pack.  One block per (net, Linear).
+// ---------------------------------------------------------------------------------------------------------------------
+struct PackArgs {
+    PjSpec spec;
+    Plan plan;
+};
+
+__global__ void pack_kernel(const __grid_constant__ PackArgs A, const float* __restrict__ theta, float* __restrict__ pack) {
+    const PjSpec& sp = A.spec;
+    const Plan& pl = A.plan;
+    const int n = blockIdx.x / PJ_MAX_LINEAR, l = blockIdx.x % PJ_MAX_LINEAR;
+    if (n >= sp.n_nets) return;
+    const PjNet& net = sp.net[n];
+    const int L = net.n_linear - 1;
+    if (l > L) return;
+    const int fin = net.width[l], fout = net.width[l + 1];
+    const float* W = theta + net.w_off[l];
+    const float* b = theta + net.b_off[l];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (l == 0) {
+        const int hp1 = pl.hp[n][1];
+        float* wt = pack + pl.s_wt0[n];
+        for (int e = tid; e < fin * hp1; e += nt) {
+            const int i = e / hp1, u = e - i * hp1;
+            wt[e] = (u < fout) ? W[u * fin + i] : 0.0f;
+        }
+        float* bp = pack + pl.s_b[n][0];
+        for (int u = tid; u < hp1; u += nt) bp[u] = (u < fout) ? b[u] : 0.0f;
+        if (L == 0) return;
+    }
+    if (l >= 1 && l < L) {
+        const int hi = pl.hp[n][l], ho = pl.hp[n][l + 1];
+        float* wt = pack + pl.b_wt[n][l];
+        float* wo = pack + pl.b_wo[n][l];
+        for (int e = tid; e < hi * ho; e += nt) {
+            const int i = e / ho, u = e - i * ho;              // K-major [in][out]
+            wt[e] = (i < fin && u < fout) ? W[u * fin + i] : 0.0f;
+            const int u2 = e / hi, i2 = e - u2 * hi;           // out-major [out][in]
+            wo[e] = (i2 < fin && u2 < fout) ? W[u2 * fin + i2] : 0.0f;
+        }
+        float* bp = pack + pl.s_b[n][l];
+        for (int u = tid; u < ho; u += nt) bp[u] = (u < fout) ? b[u] : 0.0f;
+    }
+    if (l == L) {
+        const int hpL = pl.hp[n][L];
+        float* wlt = pack + pl.s_wlt[n];
+        float* wlo = pack + pl.s_wlo[n];
+        for (int e = tid; e < hpL * fout; e += nt) {
+            const int k = e / fout, o = e - k * fout;
+            wlt[e] = (k < fin) ? W[o * fin + k] : 0.0f;
+            const int o2 = e / hpL, k2 = e - o2 * hpL;
+            wlo[e] = (k2 < fin) ? W[o2 * fin + k2] : 0.0f;
+        }
+        float* bo = pack + pl.s_bout[n];
+        for (int o = tid; o < 4; o += nt) bo[o] = (o < fout) ? b[o] : 0.0f;
+    }
+}
+
+static int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    return fail(-5, "%s: %s", what, cudaGetErrorString(e));
+}
+
+}  // namespace pj
+
+using namespace pj;
+
+extern "C" {
+
+int pj_abi_version(void) { return PJ_ABI_VERSION; }
+
+const char* pj_last_error(void) { return g_err; }
+
+int pj_sizes(const PjSpec* spec, int64_t n_points, PjSizes* out) {
+    if (!spec || !out) return fail(-1, "null argument");
+    Plan pl;
+    if (int rc = make_plan(*spec, n_points, 0, pl)) return rc;
+    out->pack_bytes = pl.pack_floats * 4;
+    out->workspace_bytes = pl.ws_bytes;
+    out->tile_points = pl.T;
+    out->grid = pl.grid;
+    out->smem_forward = pl.k1_bytes;
+    out->smem_backward = pl.k2_bytes;
+    out->launches_forward = 2;
+    out->launches_backward = 2;
+    return 0;
+}
+
+int pj_plan_info(const PjSpec* spec, int64_t n_points, int64_t* out, int32_t n_out) {
+    if (!spec || !out) return fail(-1, "null argument");
+    Plan pl;
+    if (int rc = make_plan(*spec, n_points, 0, pl)) return rc;
+    const long long head[19] = {pl.T, pl.P, pl.Q, pl.C, pl.RS, pl.n_tiles, pl.grid, pl.hmax, pl.n_stage, pl.n_stage_bwd,
+                                pl.resident_fwd, pl.resident_bwd, pl.zj_tile_floats, pl.ws_zj, pl.ws_seed, pl.ws_gpart,
+                                pl.ws_bytes, pl.k1_bytes, pl.k2_bytes};
+    int k = 0;
+    for (int i = 0; i < 19 && k < n_out; ++i) out[k++] = head[i];
+    for (int n = 0; n < PJ_MAX_NETS; ++n) {
+        for (int l = 0; l <= PJ_MAX_LINEAR && k < n_out; ++l) out[k++] = pl.hp[n][l];
+        for (int l = 0; l < PJ_MAX_LINEAR && k < n_out; ++l) out[k++] = pl.zj_off[n][l];
+    }
+    return 0;
+}
+
+int pj_pack(const PjSpec* spec, const float* theta, float* theta_pack, void* stream) {
+    if (!spec || !theta || !theta_pack) return fail(-1, "null argument");
+    PackArgs a;
+    a.spec = *spec;
+    if (int rc = make_plan(*spec, 1, 0, a.plan)) return rc;
+    pack_kernel<<<spec->n_nets * PJ_MAX_LINEAR, 256, 0, (cudaStream_t)stream>>>(a, theta, theta_pack);
+    return check_cuda(cudaGetLastError(), "pack launch");
+}
+
+static int run_k1(const PjSpec* spec, const int32_t* prog, int32_t prog_len, const float* const* coords, int64_t n,
+                  const float* theta_pack, int mode, float loss_scale, const float* rbar, float* u_out, float* r_out,
+                  float* sumsq_out, void* ws, size_t ws_bytes, void* stream) {
+    if (!spec || !prog || !coords || !theta_pack || !ws) return fail(-1, "null argument");
+    K1Args a;
+    memset(&a, 0, sizeof(a));
+    a.spec = *spec;
+    if (int rc = make_plan(*spec, n, prog_len, a.plan)) return rc;
+    const size_t need = mode == 1 ? (size_t)a.plan.ws_bytes : (size_t)LOSS_PART_BYTES;
+    if (ws_bytes < need) return fail(-1, "workspace too small: %zu < %zu bytes", ws_bytes, need);
+    if (a.plan.k1_bytes > SMEM_LIMIT) return fail(-2, "forward kernel needs %d B of shared memory", a.plan.k1_bytes);
+    for (int i = 0; i < spec->n_coords; ++i) {
+        if (!coords[i]) return fail(-1, "coords[%d] is null", i);
+        a.coords[i] = coords[i];
+    }
+    a.pack = theta_pack;
+    a.prog = reinterpret_cast<const int4*>(prog);
+    a.prog_len = prog_len;
+    a.mode = mode;
+    a.N = n;
+    a.loss_scale = loss_scale;
+    a.rbar = rbar;
+    a.u_out = u_out;
+    a.r_out = r_out;
+    char* w = static_cast<char*>(ws);
+    a.loss_part = reinterpret_cast<float*>(w + a.plan.ws_loss);
+    a.zj = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_zj) : nullptr;
+    a.seeds = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_seed) : nullptr;
+    const SchemeEntry* e = find_scheme(spec->n1, spec->n2);
+    if (int rc = check_cuda(e->k1(a, a.plan.grid, a.plan.k1_bytes, (cudaStream_t)stream), "forward launch")) return rc;
+    if (sumsq_out)
+        return check_cuda(launch_loss_finalize(a.loss_part, a.plan.grid, sumsq_out, (cudaStream_t)stream), "loss finalize");
+    return 0;
+}
+
+int pj_forward(const PjSpec* spec, const int32_t* prog_eval, int32_t prog_len, const float* const* coords,
+               int64_t n_points, const float* theta_pack, float* u_out, float* resid_out, float* sumsq_out,
+               void* workspace, size_t workspace_bytes, void* stream) {
+    return run_k1(spec, prog_eval, prog_len, coords, n_points, theta_pack, 0, 0.0f, nullptr, u_out, resid_out, sumsq_out,
+                  workspace, workspace_bytes, stream);
+}
+
+int pj_forward_train(const PjSpec* spec, const int32_t* prog_train, int32_t prog_len, const float* const* coords,
+                     int64_t n_points, const float* theta_pack, float loss_scale, const float* rbar, float* resid_out,
+                     float* sumsq_out, void* workspace, size_t workspace_bytes, void* stream) {
+    return run_k1(spec, prog_train, prog_len, coords, n_points, theta_pack, 1, loss_scale, rbar, nullptr, resid_out,
+                  sumsq_out, workspace, workspace_bytes, stream);
+}
+
+int pj_backward(const PjSpec* spec, const float* const* coords, int64_t n_points, const float* theta_pack,
+                float* grad_theta, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!spec || !coords || !theta_pack || !grad_theta || !workspace) return fail(-1, "null argument");
+    K2Args a;
+    memset(&a, 0, sizeof(a));
+    a.spec = *spec;
+    if (int rc = make_plan(*spec, n_points, 0, a.plan)) return rc;
+    if (workspace_bytes < (size_t)a.plan.ws_bytes)
+        return fail(-1, "workspace too small: %zu < %lld bytes", workspace_bytes, a.plan.ws_bytes);
+    if (a.plan.k2_bytes > SMEM_LIMIT) return fail(-2, "backward kernel needs %d B of shared memory", a.plan.k2_bytes);
+    for (int i = 0; i < spec->n_coords; ++i) a.coords[i] = coords[i];
+    a.pack = theta_pack;
+    a.N = n_points;
+    char* w = static_cast<char*>(workspace);
+    a.zj = reinterpret_cast<const float*>(w + a.plan.ws_zj);
+    a.seeds = reinterpret_cast<const float*>(w + a.plan.ws_seed);
+    a.gpart = reinterpret_cast<float*>(w + a.plan.ws_gpart);
+    const SchemeEntry* e = find_scheme(spec->n1, spec->n2);
+    if (int rc = check_cuda(e->k2(a, a.plan.grid, a.plan.k2_bytes, (cudaStream_t)stream), "backward launch")) return rc;
+    return check_cuda(launch_reduce(a.gpart, a.plan.grid, spec->n_theta, grad_theta, (cudaStream_t)stream), "reduce launch");
+}
+
+}  // extern "C"

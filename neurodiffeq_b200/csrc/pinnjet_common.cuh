@@ -1,0 +1,282 @@
+// pinnjet_common.cuh -- shared definitions of the sm_100a kernels (plan, PTX helpers, jet algebra, FFMA2 microkernels).
+//
+// Kernel family (DESIGN.md has the full picture):
+//   K0  pack      theta (torch layout) -> K-major / out-major padded copies the tiles stream with bulk TMA
+//   K1  forward   coords -> FCNN forward in Taylor (jet) mode -> re-parameterisation + residual program
+//                 (+ seeds dL/d(jet) and z-jets for K2 when training)
+//   K2  backward  one reverse sweep per tile: adjoint GEMMs + weight-gradient GEMMs, per-CTA partials
+//   K2b reduce    partials -> grad_theta (+=)
+// One persistent CTA per SM: 8 compute warps + 1 producer warp (bulk-TMA weight stream through an mbarrier ring).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pinnjet.h"
+
+#ifndef PJ_USE_FFMA2
+#define PJ_USE_FFMA2 1
+#endif
+
+namespace pj {
+
+constexpr int NT_COMPUTE = 256;          // compute threads (8 warps)
+constexpr int NT_TOTAL = 288;            // + producer warp
+constexpr int N_CWARPS = NT_COMPUTE / 32;
+constexpr int EPI_BATCH = 256;           // points per residual-program batch (one per compute thread)
+constexpr int CHUNK_FLOATS = 4096;       // weight chunk = 16 KB
+constexpr int MAX_STAGES = 8;
+constexpr int ROW_PAD = 4;               // jet rows are C*T + 4 floats: conflict-free row-strided float4 loads
+
+// opcodes of the residual program (mirror of neurodiffeq_b200/symbolic.py)
+enum : int {
+    OP_CONST = 0, OP_COORD, OP_NET, OP_RBAR, OP_PARAM, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_SIN, OP_COS, OP_EXP,
+    OP_LOG, OP_TANH, OP_SQRT, OP_ABS, OP_SIGN, OP_POWC, OP_RCP, OP_ST_U, OP_ST_R, OP_ST_SEED, OP_TAN, OP_SINH, OP_COSH,
+    OP_ATAN, OP_ERF
+};
+
+// Everything derived from (spec, N): identical on host and device, computed by make_plan() in pinnjet_api.cu.
+struct Plan {
+    int T, P, Q, C, RS;                  // tile points, thread tile, channels, jet row stride (floats)
+    int n_tiles, grid, hmax;
+    int n_stage, n_stage_bwd, resident_fwd, resident_bwd, chunks_fwd, chunks_bwd;   // n_stage: forward ring
+    int hp[PJ_MAX_NETS][PJ_MAX_LINEAR + 1];   // padded widths (hidden -> multiple of 32; input/output unpadded)
+    // ---- packed parameter copy (float offsets) ----
+    int small_floats;
+    int s_wt0[PJ_MAX_NETS];              // [n_in][hp1]       first Linear, K-major
+    int s_b[PJ_MAX_NETS][PJ_MAX_LINEAR]; // hidden biases, padded
+    int s_wlt[PJ_MAX_NETS];              // [hpL][n_out]      last Linear, K-major        (forward)
+    int s_wlo[PJ_MAX_NETS];              // [n_out][hpL]      last Linear, out-major      (backward)
+    int s_bout[PJ_MAX_NETS];
+    long long b_wt[PJ_MAX_NETS][PJ_MAX_LINEAR];   // hidden->hidden Linear l: [in_p][out_p]  (forward B operand)
+    long long b_wo[PJ_MAX_NETS][PJ_MAX_LINEAR];   //                          [out_p][in_p]  (adjoint B operand)
+    long long pack_floats;
+    // ---- small-gradient accumulators in shared memory (float offsets) ----
+    int g_w0[PJ_MAX_NETS], g_b[PJ_MAX_NETS][PJ_MAX_LINEAR], g_wl[PJ_MAX_NETS], g_bout[PJ_MAX_NETS], sgrad_floats;
+    // ---- workspace (byte offsets) ----
+    int zj_off[PJ_MAX_NETS][PJ_MAX_LINEAR];       // float offset of hidden layer h (1..L) z-jets inside a tile block
+    long long zj_tile_floats;
+    long long ws_zj, ws_seed, ws_gpart, ws_loss, ws_bytes;
+    // ---- shared memory (byte offsets) ----
+    int k1_act, k1_ring, k1_small, k1_ycache, k1_slots, k1_prog, k1_misc, k1_bytes;
+    int k2_g0, k2_g1, k2_zb, k2_ring, k2_small, k2_ybar, k2_sgrad, k2_misc, k2_bytes;
+};
+
+struct K1Args {
+    PjSpec spec;
+    Plan plan;
+    const float* coords[PJ_MAX_COORDS];
+    const float* pack;
+    const int4* prog;
+    int prog_len;
+    int mode;                            // 0 = eval (u, residual), 1 = train (residual, seeds, z-jets)
+    long long N;
+    float loss_scale;
+    const float* rbar;
+    float* u_out;
+    float* r_out;
+    float* zj;
+    float* seeds;
+    float* loss_part;
+};
+
+struct K2Args {
+    PjSpec spec;
+    Plan plan;
+    const float* coords[PJ_MAX_COORDS];
+    const float* pack;
+    long long N;
+    const float* zj;
+    const float* seeds;
+    float* gpart;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier, bulk TMA (cp.async.bulk -> SASS UBLKCP), named barriers, packed FP32 FMA (FFMA2)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk TMA global -> shared, completion signalled on an mbarrier (bytes multiple of 16, 16B-aligned both sides)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// barrier among the 256 compute threads only (the producer warp never joins)
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// packed pair of fp32 in one 64-bit register pair: the operand type of fma.rn.f32x2 (SASS FFMA2)
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack2(float x, float y) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(f2 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ void ffma2(f2& d, const f2 a, const f2 b) {
+#if PJ_USE_FFMA2
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+#else
+    const float2 x = unpack2(a), y = unpack2(b), z = unpack2(d);
+    d = pack2(fmaf(x.x, y.x, z.x), fmaf(x.y, y.y, z.y));
+#endif
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// sum over the 8 point-group lanes of a warp (lane bits 0..2)
+__device__ __forceinline__ float pg_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// activation jets.  Channels: 0 value | 1..N1 first order | N1+1..N1+N2 pure second order.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void act_d2(int act, float z0, float& a0, float& s1, float& s2) {
+    if (act == PJ_ACT_TANH) {
+        a0 = tanhf(z0);
+        s1 = fmaf(-a0, a0, 1.0f);
+        s2 = -2.0f * a0 * s1;
+    } else {
+        sincosf(z0, &a0, &s1);
+        s2 = -a0;
+    }
+}
+
+// z-jet -> a-jet, in place
+template <int N1, int N2>
+__device__ __forceinline__ void act_forward(int act, float (&z)[1 + N1 + N2]) {
+    float a0, s1, s2;
+    act_d2(act, z[0], a0, s1, s2);
+#pragma unroll
+    for (int s = 0; s < N2; ++s) z[1 + N1 + s] = fmaf(s2 * z[1 + s], z[1 + s], s1 * z[1 + N1 + s]);
+#pragma unroll
+    for (int f = 0; f < N1; ++f) z[1 + f] *= s1;
+    z[0] = a0;
+}
+
+// reverse of the activation jet: given z-jet and the adjoint of the a-jet, produce a-jet (for the weight-gradient GEMM)
+// and the adjoint of the z-jet.
+template <int N1, int N2>
+__device__ __forceinline__ void act_backward(int act, const float (&z)[1 + N1 + N2], const float (&ab)[1 + N1 + N2],
+                                             float (&a)[1 + N1 + N2], float (&zb)[1 + N1 + N2]) {
+    float a0, s1, s2, s3;
+    act_d2(act, z[0], a0, s1, s2);
+    s3 = (act == PJ_ACT_TANH) ? (-2.0f * s1 * s1 - 2.0f * a0 * s2) : -s1;
+    float zb0 = s1 * ab[0];
+#pragma unroll
+    for (int f = 0; f < N1; ++f) {
+        zb[1 + f] = s1 * ab[1 + f];
+        zb0 = fmaf(s2 * z[1 + f], ab[1 + f], zb0);
+        a[1 + f] = s1 * z[1 + f];
+    }
+#pragma unroll
+    for (int s = 0; s < N2; ++s) {
+        const float zf = z[1 + s], zs = z[1 + N1 + s], abs_ = ab[1 + N1 + s];
+        zb[1 + N1 + s] = s1 * abs_;
+        zb[1 + s] = fmaf(2.0f * s2 * zf, abs_, zb[1 + s]);
+        zb0 = fmaf(fmaf(s3 * zf, zf, s2 * zs), abs_, zb0);
+        a[1 + N1 + s] = fmaf(s2 * zf, zf, s1 * zs);
+    }
+    zb[0] = zb0;
+    a[0] = a0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// register-tile GEMM: acc[q][c][p] += sum_k A[k][c][p0+p] * B[k][u0+q]
+//   A: jet buffer rows (stride RS floats), channel c at +c*T, points contiguous       (shared memory)
+//   B: weight chunk rows (stride ldb floats), output units contiguous                  (shared memory)
+// Thread tile P points x Q units x C channels; point pairs are packed for FFMA2.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int P, int Q, int C>
+__device__ __forceinline__ void gemm_rows(f2 (&acc)[Q][C][P / 2], const float* __restrict__ a_ptr, int RS, int T,
+                                          const float* __restrict__ b_ptr, int ldb, int nrows) {
+#pragma unroll 2
+    for (int k = 0; k < nrows; ++k) {
+        f2 a[C][P / 2];
+        const float* ar = a_ptr + k * RS;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if constexpr (P == 4) {
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(ar + c * T);
+                a[c][0] = v.x;
+                a[c][1] = v.y;
+            } else {
+                a[c][0] = *reinterpret_cast<const f2*>(ar + c * T);
+            }
+        }
+        float b[Q];
+        const float* br = b_ptr + k * ldb;
+#pragma unroll
+        for (int q4 = 0; q4 < Q / 4; ++q4) {
+            const float4 v = *reinterpret_cast<const float4*>(br + 4 * q4);
+            b[4 * q4 + 0] = v.x;
+            b[4 * q4 + 1] = v.y;
+            b[4 * q4 + 2] = v.z;
+            b[4 * q4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const f2 bb = pack2(b[q], b[q]);
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int h = 0; h < P / 2; ++h) ffma2(acc[q][c][h], a[c][h], bb);
+        }
+    }
+}
+
+// scalar view of a packed accumulator tile (p is a compile-time constant after unrolling)
+template <int P>
+__device__ __forceinline__ float pick(const f2 (&v)[P / 2], int p) {
+    const float2 t = unpack2(v[p >> 1]);
+    return (p & 1) ? t.y : t.x;
+}
+
+// thread -> (point group, unit group) mapping shared by K1 and K2: a warp covers 8 point groups x 4 unit groups
+struct JobMap {
+    int p0, u0, pg_lane;
+    __device__ __forceinline__ JobMap(int tid, int T, int P, int Q) {
+        const int warp = tid >> 5, lane = tid & 31;
+        const int n_pgb = (T / P) >> 3;
+        pg_lane = lane & 7;
+        p0 = P * ((warp % n_pgb) * 8 + pg_lane);
+        u0 = Q * ((warp / n_pgb) * 4 + (lane >> 3));
+    }
+};
+
+}  // namespace pj

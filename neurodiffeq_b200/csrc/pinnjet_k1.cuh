@@ -1,0 +1,293 @@
+// pinnjet_k1.cuh -- K1: fused forward kernel (coords -> FCNN Taylor-mode jets -> re-parameterisation + residual).
+//
+// Replaces, per batch, reference solvers.py:373-383:  cond.enforce(net, *coords) (conditions.py:41-57, networks.py:68),
+// the user's diff_eqs with every diff()/operator call (neurodiffeq.py:6-34, operators.py), torch.cat and the
+// (r**2).mean() reduction -- ~170 autograd nodes and several hundred ATen launches -- by ONE launch.
+//
+// Per tile of T points a CTA keeps ALL jet channels of one hidden layer in shared memory ([unit][channel][point],
+// row stride RS) and walks the layers: the hidden->hidden contraction for the C channels is one register-tiled
+// FP32 GEMM (FFMA2, packed point pairs) whose B operand (K-major weights) is streamed by a producer warp with bulk
+// TMA through an mbarrier ring (kept resident when all layers fit).  The activation-jet rule runs on the accumulator
+// registers, results go back to shared memory in place.  The raw network-output jets of up to 256 points are
+// collected and the residual program is then interpreted with one point per thread.
+#pragma once
+#include "pinnjet_common.cuh"
+#include "pinnjet_program.cuh"
+
+namespace pj {
+
+// ---- producer warp: stream the hidden->hidden weight matrices of every tile, in consumption order -------------------
+// forward order: net 0..n-1, Linear l = 1..L-1, row chunks ascending.  backward (K2): Linear l = L-1..1.
+template <bool kForward>
+__device__ __forceinline__ void weight_producer(const PjSpec& sp, const Plan& pl, const float* __restrict__ pack,
+                                                float* ring, uint64_t* full, uint64_t* empty, int my_tiles) {
+    const bool resident = kForward ? pl.resident_fwd : pl.resident_bwd;
+    const int n_stage = kForward ? pl.n_stage : pl.n_stage_bwd;
+    const int tiles = resident ? (my_tiles > 0 ? 1 : 0) : my_tiles;
+    int it = 0;
+    for (int t = 0; t < tiles; ++t) {
+        for (int n = 0; n < sp.n_nets; ++n) {
+            const int L = sp.net[n].n_linear - 1;
+            for (int li = 1; li < L; ++li) {
+                const int l = kForward ? li : (L - li);
+                const int rows = kForward ? pl.hp[n][l] : pl.hp[n][l + 1];
+                const int cols = kForward ? pl.hp[n][l + 1] : pl.hp[n][l];
+                const float* src = pack + (kForward ? pl.b_wt[n][l] : pl.b_wo[n][l]);
+                const int rpc = CHUNK_FLOATS / cols;
+                for (int r0 = 0; r0 < rows; r0 += rpc, ++it) {
+                    const int nr = min(rpc, rows - r0);
+                    const int stage = it % n_stage;
+                    if (it >= n_stage) mbar_wait(&empty[stage], ((it / n_stage) - 1) & 1);
+                    const uint32_t bytes = (uint32_t)(nr * cols) * 4u;
+                    mbar_arrive_expect_tx(&full[stage], bytes);
+                    tma_bulk_g2s(ring + (size_t)stage * CHUNK_FLOATS, src + (size_t)r0 * cols, bytes, &full[stage]);
+                }
+            }
+        }
+    }
+}
+
+// consumer-side cursor over the same chunk sequence
+struct RingCursor {
+    int it;          // streaming: global chunk index; resident: chunk index within the tile
+    int n_stage;
+    bool resident;
+    uint64_t *full, *empty;
+    float* ring;
+    __device__ __forceinline__ const float* acquire() {
+        const int stage = it % n_stage;
+        mbar_wait(&full[stage], resident ? 0u : (uint32_t)((it / n_stage) & 1));
+        return ring + (size_t)stage * CHUNK_FLOATS;
+    }
+    __device__ __forceinline__ void release(int lane) {
+        if (!resident) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[it % n_stage]);
+        }
+        ++it;
+    }
+};
+
+template <int P, int Q, int N1, int N2>
+__global__ void __launch_bounds__(NT_TOTAL, 1) k1_forward_kernel(const __grid_constant__ K1Args A) {
+    constexpr int C = 1 + N1 + N2;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const PjSpec& sp = A.spec;
+    const Plan& pl = A.plan;
+    float* act = reinterpret_cast<float*>(smem + pl.k1_act);
+    float* ring = reinterpret_cast<float*>(smem + pl.k1_ring);
+    float* small = reinterpret_cast<float*>(smem + pl.k1_small);
+    float* ycache = reinterpret_cast<float*>(smem + pl.k1_ycache);
+    float* slots = reinterpret_cast<float*>(smem + pl.k1_slots);
+    int4* prog_s = reinterpret_cast<int4*>(smem + pl.k1_prog);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + pl.k1_misc);
+    uint64_t* empty = full + MAX_STAGES;
+    float* red = reinterpret_cast<float*>(empty + MAX_STAGES);   // [N_CWARPS] per-warp sum of r^2
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = pl.T, RS = pl.RS;
+    const int my_tiles = (pl.n_tiles > (int)blockIdx.x) ? (pl.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < MAX_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], N_CWARPS);
+        }
+        fence_barrier_init();
+    }
+    for (int i = tid; i < pl.small_floats; i += NT_TOTAL) small[i] = __ldg(A.pack + i);
+    for (int i = tid; i < A.prog_len; i += NT_TOTAL) prog_s[i] = __ldg(A.prog + i);
+    if (tid < N_CWARPS) red[tid] = 0.0f;
+    __syncthreads();
+
+    if (warp == N_CWARPS) {   // ---------------- producer warp ----------------
+        if (lane == 0) weight_producer<true>(sp, pl, A.pack, ring, full, empty, my_tiles);
+        return;
+    }
+
+    // -------------------------------------------- compute warps --------------------------------------------------------
+    const JobMap jm(tid, T, P, Q);
+    const int p0 = jm.p0, u0 = jm.u0;
+    RingCursor cur{0, pl.n_stage, pl.resident_fwd != 0, full, empty, ring};
+    const bool train = A.mode == 1;
+    float my_sumsq = 0.0f;
+    int batch_n = 0, batch_first_iter = 0;
+
+    for (int iter = 0; iter < my_tiles; ++iter) {
+        const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
+        const long long base = tile * T;
+        if (cur.resident) cur.it = 0;
+        float* zj_tile = train ? A.zj + tile * pl.zj_tile_floats : nullptr;
+
+        for (int n = 0; n < sp.n_nets; ++n) {
+            const PjNet& net = sp.net[n];
+            const int L = net.n_linear - 1;   // hidden layers
+            const int act_kind = net.act;
+
+            // ---------------- Linear 0: coordinates -> hidden 1 (first-order channels are columns of W) ----------------
+            {
+                const int hp1 = pl.hp[n][1];
+                if (u0 < hp1) {
+                    const float* wt0 = small + pl.s_wt0[n];
+                    const float* b0 = small + pl.s_b[n][0];
+                    float x[PJ_MAX_COORDS][P];
+#pragma unroll
+                    for (int i = 0; i < PJ_MAX_COORDS; ++i)
+                        if (i < net.n_in) {
+#pragma unroll
+                            for (int p = 0; p < P; ++p) {
+                                const long long g = min(base + p0 + p, A.N - 1);
+                                x[i][p] = __ldg(A.coords[net.in_coord[i]] + g);
+                            }
+                        }
+                    float* zrow = train ? zj_tile + pl.zj_off[n][1] : nullptr;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const int u = u0 + q;
+                        float w[PJ_MAX_COORDS];
+#pragma unroll
+                        for (int i = 0; i < PJ_MAX_COORDS; ++i) w[i] = (i < net.n_in) ? wt0[i * hp1 + u] : 0.0f;
+                        float dz[N1 > 0 ? N1 : 1];
+#pragma unroll
+                        for (int f = 0; f < N1; ++f) {
+                            float s = 0.0f;
+#pragma unroll
+                            for (int i = 0; i < PJ_MAX_COORDS; ++i)
+                                if (i < net.n_in) s = fmaf(w[i], sp.dir[f][net.in_coord[i]], s);
+                            dz[f] = s;
+                        }
+                        float zq[P][C];
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            float s = b0[u];
+#pragma unroll
+                            for (int i = 0; i < PJ_MAX_COORDS; ++i)
+                                if (i < net.n_in) s = fmaf(w[i], x[i][p], s);
+                            zq[p][0] = s;
+#pragma unroll
+                            for (int f = 0; f < N1; ++f) zq[p][1 + f] = dz[f];
+#pragma unroll
+                            for (int s2 = 0; s2 < N2; ++s2) zq[p][1 + N1 + s2] = 0.0f;
+                        }
+                        if (train) {
+#pragma unroll
+                            for (int c = 0; c < C; ++c)
+#pragma unroll
+                                for (int p = 0; p < P; ++p) zrow[u * RS + c * T + p0 + p] = zq[p][c];
+                        }
+#pragma unroll
+                        for (int p = 0; p < P; ++p) act_forward<N1, N2>(act_kind, zq[p]);
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+#pragma unroll
+                            for (int p = 0; p < P; ++p) act[u * RS + c * T + p0 + p] = zq[p][c];
+                    }
+                }
+            }
+            bar_compute();
+
+            // ---------------- hidden -> hidden Linears l = 1..L-1 ----------------
+            for (int l = 1; l < L; ++l) {
+                const int K = pl.hp[n][l], NO = pl.hp[n][l + 1];
+                const bool valid = u0 < NO;
+                f2 acc[Q][C][P / 2];
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+#pragma unroll
+                        for (int h = 0; h < P / 2; ++h) acc[q][c][h] = 0ull;
+                const int rpc = CHUNK_FLOATS / NO;
+                for (int r0 = 0; r0 < K; r0 += rpc) {
+                    const float* chunk = cur.acquire();
+                    if (valid) gemm_rows<P, Q, C>(acc, act + r0 * RS + p0, RS, T, chunk + u0, NO, min(rpc, K - r0));
+                    cur.release(lane);
+                }
+                bar_compute();   // every read of the previous layer's jets is done -> overwrite in place
+                if (valid) {
+                    const float* bl = small + pl.s_b[n][l];
+                    float* zrow = train ? zj_tile + pl.zj_off[n][l + 1] : nullptr;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const int u = u0 + q;
+                        const float bias = bl[u];
+                        float zq[P][C];
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+#pragma unroll
+                            for (int p = 0; p < P; ++p) zq[p][c] = pick<P>(acc[q][c], p) + (c == 0 ? bias : 0.0f);
+                        if (train) {
+#pragma unroll
+                            for (int c = 0; c < C; ++c) {
+                                if constexpr (P == 4)
+                                    *reinterpret_cast<float4*>(zrow + u * RS + c * T + p0) =
+                                        make_float4(zq[0][c], zq[1][c], zq[2][c], zq[3][c]);
+                                else
+                                    *reinterpret_cast<float2*>(zrow + u * RS + c * T + p0) =
+                                        make_float2(zq[0][c], zq[1][c]);
+                            }
+                        }
+#pragma unroll
+                        for (int p = 0; p < P; ++p) act_forward<N1, N2>(act_kind, zq[p]);
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            if constexpr (P == 4)
+                                *reinterpret_cast<float4*>(act + u * RS + c * T + p0) =
+                                    make_float4(zq[0][c], zq[1][c], zq[2][c], zq[3][c]);
+                            else
+                                *reinterpret_cast<float2*>(act + u * RS + c * T + p0) = make_float2(zq[0][c], zq[1][c]);
+                        }
+                    }
+                }
+                bar_compute();
+            }
+
+            // ---------------- last Linear: hidden L -> raw outputs, all channels, into the batch jet table -------------
+            {
+                const int hpL = pl.hp[n][L], n_out = net.width[net.n_linear];
+                const float* wl = small + pl.s_wlt[n];
+                const float* bo = small + pl.s_bout[n];
+                const int rows = n_out * C;
+                for (int e = tid; e < rows * T; e += NT_COMPUTE) {
+                    const int pt = e % T, row = e / T, o = row / C, c = row - o * C;
+                    float s = (c == 0) ? bo[o] : 0.0f;
+                    const float* ap = act + c * T + pt;
+                    for (int k = 0; k < hpL; ++k) s = fmaf(wl[k * n_out + o], ap[k * RS], s);
+                    ycache[(net.yrow0 + row) * EPI_BATCH + batch_n + pt] = s;
+                }
+            }
+            bar_compute();
+        }
+
+        // ---------------- residual program over the collected batch ----------------
+        if (batch_n == 0) batch_first_iter = iter;
+        batch_n += T;
+        if (batch_n + T > EPI_BATCH || iter == my_tiles - 1) {
+            if (tid < batch_n) {
+                const int tl = tid / T, pt = tid - tl * T;
+                const long long btile = (long long)blockIdx.x + (long long)(batch_first_iter + tl) * gridDim.x;
+                const long long gidx = btile * T + pt;
+                float* seed_tile = train ? A.seeds + btile * ((long long)sp.n_yrows * T) + pt : nullptr;
+                if (gidx < A.N) {
+                    ProgIO io{A.coords, gidx, A.N, ycache + tid, A.rbar, A.loss_scale, A.u_out, A.r_out, seed_tile, T};
+                    my_sumsq += run_program(prog_s, A.prog_len, slots + tid, io);
+                } else if (train) {
+                    for (int r = 0; r < sp.n_yrows; ++r) seed_tile[r * T] = 0.0f;   // padded points: zero adjoint
+                }
+            }
+            batch_n = 0;
+            bar_compute();
+        }
+    }
+
+    my_sumsq = warp_sum(my_sumsq);
+    if (lane == 0) red[warp] = my_sumsq;
+    bar_compute();
+    if (tid == 0) {
+        float s = 0.0f;
+        for (int w = 0; w < N_CWARPS; ++w) s += red[w];
+        A.loss_part[blockIdx.x] = s;
+    }
+}
+
+}  // namespace pj

@@ -1,0 +1,331 @@
+"""ctypes binding of ``libpinnjet.so`` (include/pinnjet.h) + the device-side state of one traced problem.
+
+PyTorch is only plumbing here: it owns the device buffers (parameters, gradients, coordinates, workspace) and the
+stream; every FLOP of the hot path runs in the hand-written kernels behind the C ABI.  There is NO fallback: if the
+shared library is missing or a launch fails, this module raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import symbolic as S
+from .tracing import TracedProblem
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "csrc", "libpinnjet.so")
+
+PJ_MAX_NETS, PJ_MAX_LINEAR, PJ_MAX_COORDS, PJ_MAX_DIRS = 4, 8, 8, 4
+SUPPORTED_SCHEMES = [(1, 0), (1, 1), (2, 0), (2, 1), (2, 2), (3, 0), (3, 3)]
+
+
+class PjNet(ctypes.Structure):
+    _fields_ = [("n_in", ctypes.c_int32), ("in_coord", ctypes.c_int32 * PJ_MAX_COORDS), ("n_linear", ctypes.c_int32),
+                ("width", ctypes.c_int32 * (PJ_MAX_LINEAR + 1)), ("act", ctypes.c_int32), ("yrow0", ctypes.c_int32),
+                ("w_off", ctypes.c_int64 * PJ_MAX_LINEAR), ("b_off", ctypes.c_int64 * PJ_MAX_LINEAR)]
+
+
+class PjSpec(ctypes.Structure):
+    _fields_ = [("abi_version", ctypes.c_int32), ("n_coords", ctypes.c_int32), ("n_nets", ctypes.c_int32),
+                ("n1", ctypes.c_int32), ("n2", ctypes.c_int32),
+                ("dir", (ctypes.c_float * PJ_MAX_COORDS) * PJ_MAX_DIRS),
+                ("n_funcs", ctypes.c_int32), ("n_eq", ctypes.c_int32), ("n_yrows", ctypes.c_int32),
+                ("n_slots", ctypes.c_int32), ("n_theta", ctypes.c_int64), ("net", PjNet * PJ_MAX_NETS)]
+
+
+class PjSizes(ctypes.Structure):
+    _fields_ = [("pack_bytes", ctypes.c_int64), ("workspace_bytes", ctypes.c_int64), ("tile_points", ctypes.c_int32),
+                ("grid", ctypes.c_int32), ("smem_forward", ctypes.c_int32), ("smem_backward", ctypes.c_int32),
+                ("launches_forward", ctypes.c_int32), ("launches_backward", ctypes.c_int32)]
+
+
+_lib = None
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen libpinnjet.so (built in-tree by ``__graft_entry__.build()`` / ``csrc/build.py``).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(f"{_LIB_PATH} is missing: build it with `python neurodiffeq_b200/csrc/build.py` "
+                           f"(needs nvcc, sm_100a).  There is no non-CUDA fallback for the fused path.")
+    lib = ctypes.CDLL(_LIB_PATH)
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+    lib.pj_abi_version.restype = ctypes.c_int
+    lib.pj_last_error.restype = ctypes.c_char_p
+    lib.pj_sizes.argtypes = [ctypes.POINTER(PjSpec), i64, ctypes.POINTER(PjSizes)]
+    lib.pj_plan_info.argtypes = [ctypes.POINTER(PjSpec), i64, ctypes.POINTER(i64), i32]
+    lib.pj_plan_info.restype = ctypes.c_int
+    lib.pj_pack.argtypes = [ctypes.POINTER(PjSpec), vp, vp, vp]
+    lib.pj_forward.argtypes = [ctypes.POINTER(PjSpec), vp, i32, ctypes.POINTER(vp), i64, vp, vp, vp, vp, vp,
+                               ctypes.c_size_t, vp]
+    lib.pj_forward_train.argtypes = [ctypes.POINTER(PjSpec), vp, i32, ctypes.POINTER(vp), i64, vp, f32, vp, vp, vp, vp,
+                                     ctypes.c_size_t, vp]
+    lib.pj_backward.argtypes = [ctypes.POINTER(PjSpec), ctypes.POINTER(vp), i64, vp, vp, vp, ctypes.c_size_t, vp]
+    for fn in (lib.pj_sizes, lib.pj_pack, lib.pj_forward, lib.pj_forward_train, lib.pj_backward):
+        fn.restype = ctypes.c_int
+    if lib.pj_abi_version() != 1:
+        raise RuntimeError("libpinnjet.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ("pj_abi_version", "pj_last_error", "pj_sizes", "pj_plan_info", "pj_pack", "pj_forward", "pj_forward_train",
+                    "pj_backward")
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {load_library().pj_last_error().decode()}")
+
+
+def pad_scheme(n1, n2):
+    """Smallest compiled channel scheme that covers (n1, n2)."""
+    best = None
+    for a, b in SUPPORTED_SCHEMES:
+        if a >= n1 and b >= n2 and (best is None or (a + b) < sum(best)):
+            best = (a, b)
+    if best is None:
+        raise NotImplementedError(f"no compiled kernel for jet channels (n1={n1}, n2={n2}); "
+                                  f"available: {SUPPORTED_SCHEMES}")
+    return best
+
+
+class FusedProblem:
+    """Device state for one (nets, conditions, diff_eqs): spec, programs, flat parameter/gradient storage, workspace."""
+
+    def __init__(self, nets, conditions, diff_eqs, n_coords, coords_for_condition=None, device=None):
+        self.lib = load_library()
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("the fused PINN engine needs a CUDA device (B200, sm_100a); none is visible")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.tp = TracedProblem(nets, conditions, diff_eqs, n_coords, coords_for_condition, pad_scheme=pad_scheme)
+        tp = self.tp
+        self.n_coords, self.n_funcs, self.n_eq = n_coords, tp.n_funcs, tp.n_eq
+        self._adopt_parameters()
+        self._build_spec()
+        dev = self.device
+        self.prog_eval = torch.from_numpy(tp.prog_eval.code.copy()).to(dev)
+        self.prog_train = torch.from_numpy(tp.prog_train.code.copy()).to(dev)
+        self._prog_train_ext = None
+        self._sizes_cache = {}
+        self.pack_buf = None
+        self.workspace = None
+        self._ws_points = 0
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.kernel_launches = 0
+
+    # ---- parameters: one flat fp32 buffer, nn.Parameters become views (torch layout preserved) ----------------------
+    def _adopt_parameters(self):
+        params = []
+        for nd in self.tp.nets:
+            nd.module.to(device=self.device, dtype=torch.float32)
+            params += nd.parameters()
+        n_theta = sum(p.numel() for p in params)
+        self.theta = torch.empty(n_theta, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros(n_theta, dtype=torch.float32, device=self.device)
+        self.offsets = []
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                self.theta[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.theta[off:off + n].view(p.shape)
+                p.grad = self.grad[off:off + n].view(p.shape)
+                self.offsets.append(off)
+                off += n
+        self.params = params
+        self.n_theta = n_theta
+
+    def parameters_linked(self):
+        """True while every nn.Parameter still aliases the flat buffers (``net.to()`` / re-assignment break it)."""
+        for p, off in zip(self.params, self.offsets):
+            if p.data_ptr() != self.theta.data_ptr() + 4 * off:
+                return False
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
+                return False
+        return True
+
+    def relink(self):
+        with torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                n = p.numel()
+                if p.data_ptr() != self.theta.data_ptr() + 4 * off:
+                    self.theta[off:off + n].copy_(p.detach().to(self.device, torch.float32).reshape(-1))
+                    p.data = self.theta[off:off + n].view(p.shape)
+                if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
+                    if p.grad is not None:
+                        self.grad[off:off + n].copy_(p.grad.detach().to(self.device, torch.float32).reshape(-1))
+                    else:
+                        self.grad[off:off + n].zero_()
+                    p.grad = self.grad[off:off + n].view(p.shape)
+
+    def _build_spec(self):
+        tp = self.tp
+        sp = PjSpec()
+        sp.abi_version = 1
+        sp.n_coords = tp.n_coords
+        sp.n_nets = len(tp.nets)
+        if sp.n_nets > PJ_MAX_NETS:
+            raise NotImplementedError(f"{sp.n_nets} distinct networks (max {PJ_MAX_NETS})")
+        sp.n1, sp.n2 = tp.scheme.n1, tp.scheme.n2
+        dirs = tp.direction_matrix()
+        for f in range(tp.scheme.n1):
+            for i in range(tp.n_coords):
+                sp.dir[f][i] = float(dirs[f, i])
+        sp.n_funcs, sp.n_eq, sp.n_yrows = tp.n_funcs, tp.n_eq, tp.n_yrows
+        sp.n_slots = max(tp.prog_eval.n_slots, tp.prog_train.n_slots, tp.prog_train_ext.n_slots)
+        sp.n_theta = self.n_theta
+        k = 0
+        for n, nd in enumerate(tp.nets):
+            net = sp.net[n]
+            net.n_in = nd.widths[0]
+            for i, c in enumerate(nd.in_coord):
+                net.in_coord[i] = c
+            net.n_linear = len(nd.linears)
+            if net.n_linear > PJ_MAX_LINEAR:
+                raise NotImplementedError(f"{net.n_linear} Linear layers (max {PJ_MAX_LINEAR})")
+            for i, w in enumerate(nd.widths):
+                net.width[i] = w
+            net.act = nd.act
+            net.yrow0 = tp.yrow0[n]
+            for l in range(net.n_linear):
+                net.w_off[l] = self.offsets[k]
+                net.b_off[l] = self.offsets[k + 1]
+                k += 2
+        self.spec = sp
+
+    @property
+    def prog_train_ext(self):
+        if self._prog_train_ext is None:
+            self._prog_train_ext = torch.from_numpy(self.tp.prog_train_ext.code.copy()).to(self.device)
+        return self._prog_train_ext
+
+    # ---- buffers ------------------------------------------------------------------------------------------------------
+    def sizes(self, n_points):
+        if n_points not in self._sizes_cache:
+            out = PjSizes()
+            with torch.cuda.device(self.device):
+                _check(self.lib.pj_sizes(ctypes.byref(self.spec), n_points, ctypes.byref(out)), "pj_sizes")
+            self._sizes_cache[n_points] = out
+        return self._sizes_cache[n_points]
+
+    def _ensure_buffers(self, n_points, train):
+        sz = self.sizes(n_points)
+        if self.pack_buf is None:
+            self.pack_buf = torch.zeros(sz.pack_bytes // 4, dtype=torch.float32, device=self.device)
+        need = sz.workspace_bytes if train else 4096
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return sz
+
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _coord_ptrs(self, coords, n_points):
+        if len(coords) != self.n_coords:
+            raise ValueError(f"expected {self.n_coords} coordinate vectors, got {len(coords)}")
+        arr = (ctypes.c_void_p * self.n_coords)()
+        keep = []
+        for i, c in enumerate(coords):
+            if c.device != self.device or c.dtype != torch.float32 or not c.is_contiguous() or c.numel() != n_points:
+                c = c.detach().to(self.device, torch.float32).reshape(-1).contiguous()
+                if c.numel() != n_points:
+                    raise ValueError("all coordinate vectors must have the same number of points")
+            keep.append(c)
+            arr[i] = c.data_ptr()
+        return arr, keep
+
+    # ---- kernels ------------------------------------------------------------------------------------------------------
+    def pack(self):
+        """K0: re-layout theta for the kernels.  Must run after every change of the parameters (optimizer step)."""
+        self._ensure_buffers(1, False)
+        _check(self.lib.pj_pack(ctypes.byref(self.spec), self.theta.data_ptr(), self.pack_buf.data_ptr(),
+                                self._stream()), "pj_pack")
+        self.kernel_launches += 1
+
+    def forward(self, coords, want_u=True, want_residual=True, want_sumsq=False, repack=True):
+        """u [n_funcs,N], residual [n_eq,N] (and sum r^2 as a 1-element device tensor) at the given points.
+        ``repack=False`` skips K0 when the caller knows the parameters did not change since the last pack."""
+        n = coords[0].numel()
+        self._ensure_buffers(n, False)
+        if repack:
+            self.pack()
+        ptrs, keep = self._coord_ptrs(coords, n)
+        u = torch.empty((self.n_funcs, n), dtype=torch.float32, device=self.device) if want_u else None
+        r = torch.empty((self.n_eq, n), dtype=torch.float32, device=self.device) if want_residual else None
+        if want_sumsq:
+            self.sumsq.zero_()
+        _check(self.lib.pj_forward(ctypes.byref(self.spec), self.prog_eval.data_ptr(), len(self.tp.prog_eval), ptrs, n,
+                                   self.pack_buf.data_ptr(), u.data_ptr() if want_u else None,
+                                   r.data_ptr() if want_residual else None,
+                                   self.sumsq.data_ptr() if want_sumsq else None,
+                                   self.workspace.data_ptr(), self.workspace.numel(), self._stream()), "pj_forward")
+        self.kernel_launches += 2 if want_sumsq else 1
+        return u, r, (self.sumsq if want_sumsq else None)
+
+    def residual_grad(self, coords, n_global=None, want_residual=False, rbar=None, sumsq_out=None, repack=True):
+        """K1(train)+K2+K2b: ``grad`` += d/dtheta mean(r^2) (or of the caller's loss when ``rbar`` = dL/dr is given);
+        returns (sum r^2 device tensor, residual or None).  mean(r^2) = sumsq / (N_global * n_eq)."""
+        n = coords[0].numel()
+        self._ensure_buffers(n, True)
+        if repack:
+            self.pack()
+        ptrs, keep = self._coord_ptrs(coords, n)
+        n_glob = n if n_global is None else n_global
+        scale = 2.0 / (float(n_glob) * self.n_eq)
+        r = torch.empty((self.n_eq, n), dtype=torch.float32, device=self.device) if want_residual else None
+        if sumsq_out is None:
+            sumsq_out = self.sumsq
+            sumsq_out.zero_()
+        prog = self.prog_train if rbar is None else self.prog_train_ext
+        prog_len = len(self.tp.prog_train if rbar is None else self.tp.prog_train_ext)
+        if rbar is not None:
+            rbar = rbar.detach().to(self.device, torch.float32).contiguous()
+            if tuple(rbar.shape) != (self.n_eq, n):
+                raise ValueError(f"rbar must have shape ({self.n_eq}, {n})")
+        _check(self.lib.pj_forward_train(ctypes.byref(self.spec), prog.data_ptr(), prog_len, ptrs, n,
+                                         self.pack_buf.data_ptr(), ctypes.c_float(scale),
+                                         rbar.data_ptr() if rbar is not None else None,
+                                         r.data_ptr() if want_residual else None, sumsq_out.data_ptr(),
+                                         self.workspace.data_ptr(), self.workspace.numel(), self._stream()),
+               "pj_forward_train")
+        _check(self.lib.pj_backward(ctypes.byref(self.spec), ptrs, n, self.pack_buf.data_ptr(), self.grad.data_ptr(),
+                                    self.workspace.data_ptr(), self.workspace.numel(), self._stream()), "pj_backward")
+        self.kernel_launches += 4
+        return sumsq_out, r
+
+    def plan_info(self, n_points):
+        """Tiling plan (diagnostics): dict with T, RS, grid, ... plus padded widths and z-jet offsets per net."""
+        n = 19 + PJ_MAX_NETS * (2 * PJ_MAX_LINEAR + 1)
+        out = (ctypes.c_int64 * n)()
+        with torch.cuda.device(self.device):
+            _check(self.lib.pj_plan_info(ctypes.byref(self.spec), n_points, out, n), "pj_plan_info")
+        keys = ("T P Q C RS n_tiles grid hmax n_stage_fwd n_stage_bwd resident_fwd resident_bwd zj_tile_floats ws_zj "
+                "ws_seed ws_gpart ws_bytes smem_fwd smem_bwd").split()
+        info = {k: int(out[i]) for i, k in enumerate(keys)}
+        k = 19
+        info["hp"], info["zj_off"] = [], []
+        for _ in range(PJ_MAX_NETS):
+            info["hp"].append([int(out[k + i]) for i in range(PJ_MAX_LINEAR + 1)])
+            k += PJ_MAX_LINEAR + 1
+            info["zj_off"].append([int(out[k + i]) for i in range(PJ_MAX_LINEAR)])
+            k += PJ_MAX_LINEAR
+        return info
+
+    # ---- debugging / tests: raw views of the workspace -----------------------------------------------------------------
+    def flat_params_numpy(self):
+        return self.theta.detach().cpu().numpy().copy()
+
+    def grads_as_list(self):
+        return [self.grad[o:o + p.numel()].view(p.shape).detach().cpu().numpy().copy()
+                for p, o in zip(self.params, self.offsets)]

@@ -729,6 +729,13 @@ class ChannelScheme:
         self.n1, self.n2 = len(self.dirs), len(sec_sorted)
         self.n_coords = n_coords
 
+    def pad_to(self, n1, n2):
+        """Add inert channels (zero direction vectors / unused second-order slots) up to a compiled (n1, n2)."""
+        if n1 < self.n1 or n2 < self.n2 or n2 > n1:
+            raise ValueError("cannot shrink a channel scheme")
+        self.dirs = list(self.dirs) + [tuple([0.0] * self.n_coords)] * (n1 - self.n1)
+        self.n1, self.n2 = n1, n2
+
     @staticmethod
     def _axis(n_coords, i):
         v = [0.0] * n_coords

@@ -74,7 +74,7 @@ class NetDescription:
 
 
 class TracedProblem:
-    def __init__(self, nets, conditions, diff_eqs, n_coords, coords_for_condition=None):
+    def __init__(self, nets, conditions, diff_eqs, n_coords, coords_for_condition=None, pad_scheme=None):
         """``nets[k]`` / ``conditions[k]`` as in the reference solver; ``diff_eqs(*funcs, *coords)``.
         ``coords_for_condition(k, cond, coords) -> tuple`` lets SolverSpherical trim coordinates
         (reference solvers.py:894-916)."""
@@ -103,6 +103,8 @@ class TracedProblem:
                 raise ValueError(f"condition selects output unit {o} of a network with "
                                  f"{self.nets[net_idx].n_out} outputs")
         self.scheme = S.ChannelScheme(n_coords, [n.imm[2] for n in leaves])
+        if pad_scheme is not None:  # round the scheme up to one the engine has a compiled kernel for
+            self.scheme.pad_to(*pad_scheme(self.scheme.n1, self.scheme.n2))
         C = self.scheme.n_channels
         self.yrow0 = []
         row = 0

@@ -1,0 +1,89 @@
+"""Shared helpers of the parity tests (product namespace, oracle runs)."""
+import types
+
+import numpy as np
+import torch
+
+import workloads
+
+
+def product_namespace():
+    from neurodiffeq_b200 import diff
+    from neurodiffeq_b200 import operators as ops
+    from neurodiffeq_b200.networks import FCNN, SinActv
+    from neurodiffeq_b200 import conditions as c
+    return types.SimpleNamespace(
+        diff=diff, FCNN=FCNN, SinActv=SinActv, IVP=c.IVP, BundleIVP=c.BundleIVP, DirichletBVP2D=c.DirichletBVP2D,
+        IBVP1D=c.IBVP1D, DirichletBVPSpherical=c.DirichletBVPSpherical, NoCondition=c.NoCondition,
+        spherical_laplacian=ops.spherical_laplacian, laplacian=ops.laplacian, grad=ops.grad, div=ops.div,
+        curl=ops.curl)
+
+
+def distinct(nets):
+    seen, out = set(), []
+    for n in nets:
+        if id(n) not in seen:
+            seen.add(id(n))
+            out.append(n)
+    return out
+
+
+def set_params(nets, arrays):
+    it = iter(arrays)
+    with torch.no_grad():
+        for m in distinct(nets):
+            for p in m.parameters():
+                p.copy_(torch.as_tensor(next(it), dtype=p.dtype).reshape(p.shape))
+
+
+def get_params(nets):
+    return [p.detach().cpu().numpy().copy() for m in distinct(nets) for p in m.parameters()]
+
+
+def build_fused(key, params=None, seed=0, device=None):
+    """The product: trace the workload with neurodiffeq_b200's own classes and put it on the GPU."""
+    from neurodiffeq_b200.engine import FusedProblem
+    wl = workloads.build(product_namespace(), key)
+    torch.manual_seed(seed)
+    nets, conds = wl.make_nets(), wl.make_conditions()
+    if params is not None:
+        set_params(nets, params)
+    fp = FusedProblem(nets, conds, workloads.bundle_eq_wrapper(wl), len(wl.coord_names), device=device)
+    return wl, nets, conds, fp
+
+
+def oracle_eval(key, params, coords, dtype=torch.float64, backward=True):
+    """The CPU oracle (autograd restatement of the reference) on the same parameters / points."""
+    from oracle import reference_port as oracle
+    wl = workloads.build(oracle.NAMESPACE, key)
+    nets, conds = wl.make_nets(), wl.make_conditions()
+    oracle.load_params(nets, params, dtype=dtype)
+    return oracle.evaluate(nets, conds, workloads.bundle_eq_wrapper(wl), coords, dtype=dtype, backward=backward)
+
+
+def rel_l2(a_list, b_list):
+    num = np.sqrt(sum(((np.asarray(a, dtype=np.float64).reshape(-1) - np.asarray(b, dtype=np.float64).reshape(-1)) ** 2).sum()
+                      for a, b in zip(a_list, b_list)))
+    den = np.sqrt(sum((np.asarray(b, dtype=np.float64) ** 2).sum() for b in b_list))
+    return num / max(den, 1e-300)
+
+
+# Parity tolerances: fp32 kernels against the fp64 reference/oracle on identical fp32 inputs.
+TOL_RESID = 2e-5      # max|dr| <= TOL_RESID * rms(r) + 1e-6
+TOL_LOSS = 1e-5       # relative
+TOL_GRAD = 1e-4       # relative L2 over all parameters
+TOL_U_RTOL, TOL_U_ATOL = 1e-5, 1e-6
+
+
+def assert_parity(got_u, got_r, got_loss, got_grads, ref, label=""):
+    rms = np.sqrt((ref["residual"] ** 2).mean())
+    if got_u is not None:
+        np.testing.assert_allclose(got_u, ref["u"], rtol=TOL_U_RTOL, atol=TOL_U_ATOL, err_msg=f"{label} u")
+    if got_r is not None:
+        err = np.abs(got_r - ref["residual"]).max()
+        assert err <= TOL_RESID * rms + 1e-6, f"{label} residual: max|dr|={err:.3e} rms={rms:.3e}"
+    if got_loss is not None:
+        assert abs(got_loss - ref["loss"]) <= TOL_LOSS * abs(ref["loss"]), f"{label} loss {got_loss} vs {ref['loss']}"
+    if got_grads is not None:
+        e = rel_l2(got_grads, ref["grads"])
+        assert e <= TOL_GRAD, f"{label} grad rel-L2 {e:.3e}"

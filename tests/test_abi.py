@@ -1,0 +1,45 @@
+"""CPU: the C-ABI library loads and exports every symbol include/pinnjet.h declares (no compute calls without a GPU);
+the ctypes mirror of PjSpec has the size the C compiler gives the struct."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    sys.path.insert(0, ROOT)
+    from neurodiffeq_b200.csrc import build as pj_build
+    lib_path = pj_build.build()
+    header = open(os.path.join(ROOT, "include", "pinnjet.h")).read()
+    declared = set(re.findall(r"\b(pj_[a-z_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(lib_path)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} not exported"
+    from neurodiffeq_b200 import engine
+    assert set(engine.EXPORTED_SYMBOLS) == declared
+    assert lib.pj_abi_version() == 1
+
+
+def test_ctypes_struct_layout_matches_c(tmp_path):
+    from neurodiffeq_b200 import engine
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "pinnjet.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(PjNet), '
+                   'sizeof(PjSpec), sizeof(PjSizes));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    a, b, c = map(int, subprocess.check_output([str(exe)]).split())
+    assert (a, b, c) == (ctypes.sizeof(engine.PjNet), ctypes.sizeof(engine.PjSpec), ctypes.sizeof(engine.PjSizes))
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    import pytest
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from helpers import build_fused
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        build_fused("c2")
