@@ -1,0 +1,388 @@
+"""bench.py -- collocation-points/sec for one residual+gradient evaluation (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--points P] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic collocation points: K0 pack -> K1 (forward jets +
+residual + seeds) -> loss finalize -> K2 (reverse pass) -> K2b (reduce); with N > 1 GPUs every rank owns its own
+shard of points (weak scaling: per-GPU points fixed) and the flat [grad | sum r^2] buffer is all-reduced once per
+step over NCCL.  Workload = BASELINE.json configs[1]: Solver2D Laplace, DirichletBVP2D, FCNN(2-64-64-64-1, tanh),
+16384 points per GPU, synthetic uniform points, PyTorch-default random init.
+
+Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB memset) before every timed step,
+max over ranks.  `value` = points/s with inputs resident in HBM; `e2e` = same metric through FusedProblem's public
+call with pinned HOST coordinates copied in and the loss copied out inside the timed region.
+
+`--impl reference` times the CPU oracle port of the reference's closure (oracle/reference_port.py, torch autograd,
+float64 = the reference's default dtype) on this box's host cores for the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import workloads  # noqa: E402
+
+METRIC = "collocation-points/sec (residual+grad)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--points", type=int, default=0, help="points per GPU (default: the workload's BASELINE size)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference closure (only place outside tests/ that executes oracle/)
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_throughput(key, n_points, seconds, dtype=torch.float64, max_steps=None, warmup=1):
+    from oracle import reference_port as oracle
+    wl = workloads.build(oracle.NAMESPACE, key)
+    torch.manual_seed(0)
+    nets, conds = wl.make_nets(), wl.make_conditions()
+    for m in oracle.distinct_modules(nets):
+        m.to(dtype)
+    coords_np = workloads.sample_coords(wl, n_points, seed=0)
+    eqs = workloads.bundle_eq_wrapper(wl)
+
+    def step():
+        for m in oracle.distinct_modules(nets):
+            for p in m.parameters():
+                p.grad = None
+        coords = [torch.as_tensor(c, dtype=dtype).reshape(-1, 1).requires_grad_(True) for c in coords_np]
+        _, _, loss = oracle.closure(nets, conds, eqs, coords, backward=True)
+        return float(loss.detach())
+
+    # "all the host threads it can use": torch's intra-op pool degrades badly when oversubscribed on these small
+    # matrices (128 threads: 18 s/closure on the GPU box vs 0.12 s with 8), so the reference arm gets the thread count
+    # that is fastest for it, found by a short sweep, and that count is what `cores` reports.
+    ncpu = os.cpu_count() or 1
+    best_t, best_dt = 1, float("inf")
+    for nt in sorted({t for t in (4, 8, 16, 32, 64, ncpu) if t <= ncpu}):
+        torch.set_num_threads(nt)
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if dt < best_dt:
+            best_t, best_dt = nt, dt
+        if dt > 4 * best_dt:
+            break
+    torch.set_num_threads(best_t)
+    for _ in range(warmup):
+        step()
+    times = []
+    t_end = time.perf_counter() + seconds
+    while True:
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if (max_steps and len(times) >= max_steps) or (not max_steps and time.perf_counter() > t_end):
+            break
+    med = float(np.median(times))
+    return dict(value=n_points / med, unit="points/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{len(times)} closures of {n_points} points, {str(dtype).replace('torch.', '')}, median "
+                       f"{med * 1e3:.1f} ms, oracle/reference_port.py (torch {torch.__version__} autograd, CPU)",
+                ms_per_step=med * 1e3, steps=len(times))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = workloads.build(__import__("helpers").product_namespace(), args.workload)
+    n = args.points or wl.default_n
+    res = cpu_reference_throughput(args.workload, n, seconds=1e9, max_steps=max(args.steps, 1),
+                                   warmup=max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "points/s", "n_gpus": args.gpus,
+        "steps": res["steps"], "warmup": max(args.warmup, 1), "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{wl.name} {wl.solver} N={n} (reference closure solvers.py:369-395, CPU port)",
+                   "points_per_step": n},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(r for r in self.reasons if r != "gpu_idle"),
+                "power_w_max": max(self.power) if self.power else None, "samples": len(self.samples)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops", 1590.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import ctypes
+    from helpers import build_fused
+    from neurodiffeq_b200 import engine as E
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    wl, nets, conds, fp = build_fused(args.workload, seed=0, device=dev)
+    n = args.points or wl.default_n                       # points per GPU (weak scaling)
+    n_global = n * world
+    coords_np = workloads.sample_coords(wl, n, seed=1000 + rank)
+    coords = [torch.from_numpy(c).to(dev) for c in coords_np]
+    host_coords = [torch.from_numpy(c).pin_memory() for c in coords_np]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_body():
+        fp.gradbuf.zero_()                                # optimizer.zero_grad() + loss accumulator
+        fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq)
+        if world > 1:
+            dist.all_reduce(fp.gradbuf)
+
+    # warm-up (also sizes buffers, sets kernel attributes)
+    for _ in range(max(args.warmup, 3)):
+        step_body()
+    torch.cuda.synchronize()
+
+    graph = None
+    if not args.no_graph and world == 1:
+        graph = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        with torch.cuda.graph(graph):
+            step_body()
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step_body()
+
+    launches_per_step = 1 + 5   # gradbuf fill (torch) is not ours; pack, K1, loss-finalize, K2, K2b are
+    ours_per_step = 5
+
+    # ---- timed region: K steps, L2 flushed before each, CUDA events per step, max over ranks -------------------------
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clk:
+        t_wall0 = time.perf_counter()
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            run_step()
+            b.record()
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = float(step_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        dist.barrier()
+    ms_per_step = total_ms / args.steps
+    value = n_global / (ms_per_step * 1e-3)
+    loss = float(fp.sumsq.item()) / (n_global * fp.n_eq)
+
+    # ---- per-kernel timing for the roofline (events around each launch, same stream) ---------------------------------
+    info = fp.plan_info(n)
+    ptrs, keep = fp._coord_ptrs(coords, n)
+    sp = ctypes.byref(fp.spec)
+    cs = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+    scale = ctypes.c_float(2.0 / (n_global * fp.n_eq))
+
+    def k1_only():
+        E._check(fp.lib.pj_forward_train(sp, fp.prog_train.data_ptr(), len(fp.tp.prog_train), ptrs, n,
+                                         fp.pack_buf.data_ptr(), scale, None, None, None, fp.workspace.data_ptr(),
+                                         fp.workspace.numel(), cs()), "k1")
+
+    def k2_only():
+        E._check(fp.lib.pj_backward(sp, ptrs, n, fp.pack_buf.data_ptr(), fp.grad.data_ptr(), fp.workspace.data_ptr(),
+                                    fp.workspace.numel(), cs()), "k2")
+
+    def time_kernel(fn, reps):
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts)), float(np.min(ts))
+
+    reps = min(max(args.steps, 10), 100)
+    k1_ms, k1_min = time_kernel(k1_only, reps)
+    k2_ms, k2_min = time_kernel(k2_only, reps)   # K2 + K2b (z-jets come from the preceding K1, L2 flushed in between)
+
+    # ---- e2e: host coordinates in, loss out, through the public call -------------------------------------------------
+    def e2e_step():
+        dev_coords = [h.to(dev, non_blocking=True) for h in host_coords]
+        fp.gradbuf.zero_()
+        fp.residual_grad(dev_coords, n_global=n_global, sumsq_out=fp.sumsq)
+        if world > 1:
+            dist.all_reduce(fp.gradbuf)
+        return fp.sumsq.item()   # device -> host read of the step's result
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = min(args.steps, 100)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    b.record()
+    torch.cuda.synchronize()
+    e2e_ms = a.elapsed_time(b) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = n_global / (e2e_ms * 1e-3)
+    h2d = int(sum(h.numel() * 4 for h in host_coords))
+
+    # ---- roofline of the forward+jet kernel (K1), algorithmic FLOPs / measured launch time ----------------------------
+    bf16_peak, hbm_peak, peak_src = load_peaks()
+    clocks = clk.summary()
+    flops_k1 = wl.flops_fwdjet * n
+    ach_k1 = flops_k1 / (k1_ms * 1e-3) / 1e12
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    fp32_peak = n_sms * 128 * 2 * sm_mhz * 1e6 / 1e12       # FFMA lanes x 2 flop x clock under load
+    roofline = {
+        "kernel": "k1_forward_kernel (forward + jets + residual program)", "bound": "tensor", "achieved": ach_k1,
+        "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach_k1 / bf16_peak, "traffic": None,
+        "peak_source": f"dense bf16 tensor, {peak_src}",
+        "pipe": "fp32 FFMA2 on CUDA cores (fp32 parity; tensor cores would need 3xTF32 split, see DESIGN.md)",
+        "fp32_ffma_peak": fp32_peak, "frac_of_fp32_ffma_peak": ach_k1 / fp32_peak,
+        "algorithmic_flops_per_point": wl.flops_fwdjet, "launch_ms": k1_ms, "launch_ms_min": k1_min,
+        "k2": {"kernel": "k2_backward_kernel + k2_reduce_kernel", "algorithmic_flops_per_point": 2 * wl.flops_fwdjet,
+               "launch_ms": k2_ms, "achieved": 2 * flops_k1 / (k2_ms * 1e-3) / 1e12,
+               "frac_of_fp32_ffma_peak": 2 * flops_k1 / (k2_ms * 1e-3) / 1e12 / fp32_peak},
+    }
+
+    cpu_base = None
+    if rank == 0 and world == 1:
+        cpu_base = cpu_reference_throughput(args.workload, n, seconds=args.cpu_seconds)
+        cpu_base = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl.name}: {wl.solver}, nets {wl.nets_spec}, {n} points/GPU, "
+                                   f"residual+grad step = pack+K1+finalize+K2+K2b"
+                                   + (" + NCCL all-reduce of [grad|loss]" if world > 1 else ""),
+                       "points_per_gpu": n, "global_points": n_global, "tile_points": info["T"],
+                       "grid": info["grid"], "l2": "flushed (256 MiB memset) before every timed step",
+                       "cuda_graph": graph is not None, "parallelism": f"dp{world} (points sharded)"},
+            "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": ours_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
+            "loss": loss, "wall_s_timed_region": t_wall,
+            "step_ms_stats": {"min": float(step_ms.min()), "median": float(np.median(step_ms)),
+                              "max": float(step_ms.max())},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -112,6 +112,7 @@ static int make_plan(const PjSpec& sp, long long N, int prog_len, Plan& pl) {
         const PjNet& net = sp.net[n];
         const int L = net.n_linear - 1, n_out = net.width[net.n_linear];
         pl.s_wt0[n] = off; off += round_up(net.n_in * pl.hp[n][1], 4);
+        pl.s_dz[n] = off; off += PJ_MAX_DIRS * pl.hp[n][1];
         for (int l = 0; l < L; ++l) { pl.s_b[n][l] = off; off += pl.hp[n][l + 1]; }
         pl.s_wlt[n] = off; off += round_up(pl.hp[n][L] * n_out, 4);
         pl.s_wlo[n] = off; off += round_up(pl.hp[n][L] * n_out, 4);
@@ -142,7 +143,8 @@ static int make_plan(const PjSpec& sp, long long N, int prog_len, Plan& pl) {
         pl.g_wl[n] = off; off += n_out * pl.hp[n][L];
         pl.g_bout[n] = off; off += 4;
     }
-    pl.sgrad_floats = off;
+    pl.sgrad_floats = round_up(off, 4);
+    pl.sgrad_copies = (pl.T / pl.P) / 8;
 
     // ---- workspace ----
     long long zt = 0;
@@ -181,7 +183,7 @@ static int make_plan(const PjSpec& sp, long long N, int prog_len, Plan& pl) {
     }
     {   // K2: G | G2 | Zb | ring | small | ybar | sgrad | misc
         const int ybar_bytes = round_up(PJ_MAX_NETS * C * pl.T * 4, 128);
-        const int sgrad_bytes = round_up(pl.sgrad_floats * 4, 128);
+        const int sgrad_bytes = round_up(pl.sgrad_floats * pl.sgrad_copies * 4, 128);
         const int fixed = 3 * jet_bytes + small_bytes + ybar_bytes + sgrad_bytes + misc_bytes;
         int ns = (SMEM_LIMIT - fixed) / (CHUNK_FLOATS * 4);
         if (ns > MAX_STAGES) ns = MAX_STAGES;
@@ -234,7 +236,14 @@ __global__ void pack_kernel(const __grid_constant__ PackArgs A, const float* __r
         }
         float* bp = pack + pl.s_b[n][0];
         for (int u = tid; u < hp1; u += nt) bp[u] = (u < fout) ? b[u] : 0.0f;
-        if (L == 0) return;
+        float* dz = pack + pl.s_dz[n];   // first-order channel seeds of layer 1: W0 . dir_f (same for every point)
+        for (int e = tid; e < PJ_MAX_DIRS * hp1; e += nt) {
+            const int f = e / hp1, u = e - f * hp1;
+            float v = 0.0f;
+            if (u < fout && f < sp.n1)
+                for (int i = 0; i < fin; ++i) v = fmaf(W[u * fin + i], sp.dir[f][net.in_coord[i]], v);
+            dz[e] = v;
+        }
     }
     if (l >= 1 && l < L) {
         const int hi = pl.hp[n][l], ho = pl.hp[n][l + 1];

@@ -42,6 +42,7 @@ struct Plan {
     // ---- packed parameter copy (float offsets) ----
     int small_floats;
     int s_wt0[PJ_MAX_NETS];              // [n_in][hp1]       first Linear, K-major
+    int s_dz[PJ_MAX_NETS];               // [PJ_MAX_DIRS][hp1] first-order seeds  W0 . dir_f  (point independent)
     int s_b[PJ_MAX_NETS][PJ_MAX_LINEAR]; // hidden biases, padded
     int s_wlt[PJ_MAX_NETS];              // [hpL][n_out]      last Linear, K-major        (forward)
     int s_wlo[PJ_MAX_NETS];              // [n_out][hpL]      last Linear, out-major      (backward)
@@ -51,6 +52,7 @@ struct Plan {
     long long pack_floats;
     // ---- small-gradient accumulators in shared memory (float offsets) ----
     int g_w0[PJ_MAX_NETS], g_b[PJ_MAX_NETS][PJ_MAX_LINEAR], g_wl[PJ_MAX_NETS], g_bout[PJ_MAX_NETS], sgrad_floats;
+    int sgrad_copies;                    // one private copy per point-group block of warps (no atomics)
     // ---- workspace (byte offsets) ----
     int zj_off[PJ_MAX_NETS][PJ_MAX_LINEAR];       // float offset of hidden layer h (1..L) z-jets inside a tile block
     long long zj_tile_floats;
@@ -195,8 +197,16 @@ template <int N1, int N2>
 __device__ __forceinline__ void act_backward(int act, const float (&z)[1 + N1 + N2], const float (&ab)[1 + N1 + N2],
                                              float (&a)[1 + N1 + N2], float (&zb)[1 + N1 + N2]) {
     float a0, s1, s2, s3;
-    act_d2(act, z[0], a0, s1, s2);
-    s3 = (act == PJ_ACT_TANH) ? (-2.0f * s1 * s1 - 2.0f * a0 * s2) : -s1;
+    if (act == PJ_ACT_TANH) {   // record channel 0 = tanh(z0), stored by K1: no transcendental in the reverse pass
+        a0 = z[0];
+        s1 = fmaf(-a0, a0, 1.0f);
+        s2 = -2.0f * a0 * s1;
+        s3 = -2.0f * s1 * s1 - 2.0f * a0 * s2;
+    } else {
+        sincosf(z[0], &a0, &s1);
+        s2 = -a0;
+        s3 = -s1;
+    }
     float zb0 = s1 * ab[0];
 #pragma unroll
     for (int f = 0; f < N1; ++f) {

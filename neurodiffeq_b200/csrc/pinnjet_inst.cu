@@ -9,29 +9,41 @@ namespace pj {
 
 #if PJ_N1 < 0
 
-// K2b: grad_theta[i] += sum over CTAs of partial[cta][i]   (fixed order -> run-to-run reproducible)
+// K2b: grad_theta[i] += sum over CTAs of partial[cta][i].  Block = 64 parameters x 4 groups of partials; fixed summation
+// order -> run-to-run reproducible.
 __global__ void k2_reduce_kernel(const float* __restrict__ gpart, int n_parts, long long n_theta,
                                  float* __restrict__ grad) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_theta) return;
+    __shared__ float red[4][64];
+    const int il = threadIdx.x & 63, g = threadIdx.x >> 6;
+    const long long i = (long long)blockIdx.x * 64 + il;
     float s = 0.0f;
-    for (int p = 0; p < n_parts; ++p) s += gpart[(size_t)p * n_theta + i];
-    grad[i] += s;
+    if (i < n_theta) {
+        const int per = (n_parts + 3) / 4, p_lo = g * per, p_hi = min(n_parts, p_lo + per);
+        float s0 = 0.0f, s1 = 0.0f;
+        int p = p_lo;
+        for (; p + 1 < p_hi; p += 2) {
+            s0 += gpart[(size_t)p * n_theta + i];
+            s1 += gpart[(size_t)(p + 1) * n_theta + i];
+        }
+        if (p < p_hi) s0 += gpart[(size_t)p * n_theta + i];
+        s = s0 + s1;
+    }
+    red[g][il] = s;
+    __syncthreads();
+    if (g == 0 && i < n_theta) grad[i] += (red[0][il] + red[1][il]) + (red[2][il] + red[3][il]);
 }
 
 // sum of the per-CTA sums of squared residuals (fixed order) -> *out += total
 __global__ void loss_finalize_kernel(const float* __restrict__ part, int n_parts, float* __restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        float s = 0.0f;
-        for (int p = 0; p < n_parts; ++p) s += part[p];
-        out[0] += s;
-    }
+    float s = 0.0f;
+    for (int p = threadIdx.x; p < n_parts; p += 32) s += part[p];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[0] += s;
 }
 
-
 cudaError_t launch_reduce(const float* gpart, int n_parts, long long n_theta, float* grad, cudaStream_t s) {
-    const int nt = 256;
-    k2_reduce_kernel<<<(unsigned)((n_theta + nt - 1) / nt), nt, 0, s>>>(gpart, n_parts, n_theta, grad);
+    k2_reduce_kernel<<<(unsigned)((n_theta + 63) / 64), 256, 0, s>>>(gpart, n_parts, n_theta, grad);
     return cudaGetLastError();
 }
 cudaError_t launch_loss_finalize(const float* part, int n_parts, float* out, cudaStream_t s) {

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k1_forward_kernel(const __grid_co
                 if (u0 < hp1) {
                     const float* wt0 = small + pl.s_wt0[n];
                     const float* b0 = small + pl.s_b[n][0];
+                    const float* dzt = small + pl.s_dz[n];
                     float x[PJ_MAX_COORDS][P];
 #pragma unroll
                     for (int i = 0; i < PJ_MAX_COORDS; ++i)
@@ -149,13 +150,7 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k1_forward_kernel(const __grid_co
                         for (int i = 0; i < PJ_MAX_COORDS; ++i) w[i] = (i < net.n_in) ? wt0[i * hp1 + u] : 0.0f;
                         float dz[N1 > 0 ? N1 : 1];
 #pragma unroll
-                        for (int f = 0; f < N1; ++f) {
-                            float s = 0.0f;
-#pragma unroll
-                            for (int i = 0; i < PJ_MAX_COORDS; ++i)
-                                if (i < net.n_in) s = fmaf(w[i], sp.dir[f][net.in_coord[i]], s);
-                            dz[f] = s;
-                        }
+                        for (int f = 0; f < N1; ++f) dz[f] = dzt[f * hp1 + u];
                         float zq[P][C];
 #pragma unroll
                         for (int p = 0; p < P; ++p) {
@@ -169,14 +164,24 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k1_forward_kernel(const __grid_co
 #pragma unroll
                             for (int s2 = 0; s2 < N2; ++s2) zq[p][1 + N1 + s2] = 0.0f;
                         }
+                        // workspace record for K2: channels >= 1 are z-jets; channel 0 is tanh(z0) for tanh nets (so that
+                        // the reverse pass needs no transcendental) and z0 for sin nets
+                        float z0s[P];
+#pragma unroll
+                        for (int p = 0; p < P; ++p) z0s[p] = zq[p][0];
                         if (train) {
 #pragma unroll
-                            for (int c = 0; c < C; ++c)
+                            for (int c = 1; c < C; ++c)
 #pragma unroll
                                 for (int p = 0; p < P; ++p) zrow[u * RS + c * T + p0 + p] = zq[p][c];
                         }
 #pragma unroll
                         for (int p = 0; p < P; ++p) act_forward<N1, N2>(act_kind, zq[p]);
+                        if (train) {
+#pragma unroll
+                            for (int p = 0; p < P; ++p)
+                                zrow[u * RS + p0 + p] = (act_kind == PJ_ACT_TANH) ? zq[p][0] : z0s[p];
+                        }
 #pragma unroll
                         for (int c = 0; c < C; ++c)
 #pragma unroll
@@ -216,9 +221,12 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k1_forward_kernel(const __grid_co
                         for (int c = 0; c < C; ++c)
 #pragma unroll
                             for (int p = 0; p < P; ++p) zq[p][c] = pick<P>(acc[q][c], p) + (c == 0 ? bias : 0.0f);
+                        float z0s[P];
+#pragma unroll
+                        for (int p = 0; p < P; ++p) z0s[p] = zq[p][0];
                         if (train) {
 #pragma unroll
-                            for (int c = 0; c < C; ++c) {
+                            for (int c = 1; c < C; ++c) {
                                 if constexpr (P == 4)
                                     *reinterpret_cast<float4*>(zrow + u * RS + c * T + p0) =
                                         make_float4(zq[0][c], zq[1][c], zq[2][c], zq[3][c]);
@@ -229,6 +237,16 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k1_forward_kernel(const __grid_co
                         }
 #pragma unroll
                         for (int p = 0; p < P; ++p) act_forward<N1, N2>(act_kind, zq[p]);
+                        if (train) {
+                            const bool th = act_kind == PJ_ACT_TANH;
+                            if constexpr (P == 4)
+                                *reinterpret_cast<float4*>(zrow + u * RS + p0) =
+                                    make_float4(th ? zq[0][0] : z0s[0], th ? zq[1][0] : z0s[1], th ? zq[2][0] : z0s[2],
+                                                th ? zq[3][0] : z0s[3]);
+                            else
+                                *reinterpret_cast<float2*>(zrow + u * RS + p0) =
+                                    make_float2(th ? zq[0][0] : z0s[0], th ? zq[1][0] : z0s[1]);
+                        }
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
                             if constexpr (P == 4)

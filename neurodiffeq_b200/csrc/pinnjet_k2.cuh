@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
         fence_barrier_init();
     }
     for (int i = tid; i < pl.small_floats; i += NT_TOTAL) small[i] = __ldg(A.pack + i);
-    for (int i = tid; i < pl.sgrad_floats; i += NT_TOTAL) sgrad[i] = 0.0f;
+    for (int i = tid; i < pl.sgrad_floats * pl.sgrad_copies; i += NT_TOTAL) sgrad[i] = 0.0f;
     for (long long i = tid; i < sp.n_theta; i += NT_TOTAL) gpart[i] = 0.0f;
     __syncthreads();
 
@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
 
     const JobMap jm(tid, T, P, Q);
     const int p0 = jm.p0, u0 = jm.u0;
+    // every (point-group block, unit) pair is owned by exactly one lane -> private accumulation, no atomics
+    float* sg = sgrad + (size_t)(warp % ((T / P) >> 3)) * pl.sgrad_floats;
     RingCursor cur{0, pl.n_stage_bwd, pl.resident_bwd != 0, full, empty, ring};
     uint32_t zphase = 0;
     // lane mapping of the weight-gradient GEMM: 8 k-lanes x 4 j-lanes per warp
@@ -156,10 +158,10 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
                         for (int o = 0; o < PJ_MAX_NETS; ++o)
                             if (o < n_out) gw[o] = pg_sum(gw[o]);
                         if (jm.pg_lane == 0) {
-                            atomicAdd(&sgrad[pl.g_b[n][L - 1] + u], gb);
+                            sg[pl.g_b[n][L - 1] + u] += gb;
 #pragma unroll
                             for (int o = 0; o < PJ_MAX_NETS; ++o)
-                                if (o < n_out) atomicAdd(&sgrad[pl.g_wl[n] + o * hpL + u], gw[o]);
+                                if (o < n_out) sg[pl.g_wl[n] + o * hpL + u] += gw[o];
                         }
                     }
                 }
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
                             }
                         }
                         gb = pg_sum(gb);
-                        if (jm.pg_lane == 0) atomicAdd(&sgrad[pl.g_b[n][h - 2] + u], gb);
+                        if (jm.pg_lane == 0) sg[pl.g_b[n][h - 2] + u] += gb;
                     }
                 }
                 bar_compute();
@@ -241,10 +243,15 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
                     for (int wt = warp; wt < n_kb * n_jb; wt += N_CWARPS) {
                         const int jb = (wt / n_kb) * 16, kb = (wt % n_kb) * 32;
                         f2 wacc[WJ][WK];
+                        float old[WJ][WK];   // running partial of this thread's 4x4 outputs: loads overlap the GEMM
 #pragma unroll
                         for (int i = 0; i < WJ; ++i)
 #pragma unroll
-                            for (int j = 0; j < WK; ++j) wacc[i][j] = 0ull;
+                            for (int jj = 0; jj < WK; ++jj) {
+                                wacc[i][jj] = 0ull;
+                                const int j = jb + jl + 4 * i, k = kb + kl + 8 * jj;
+                                old[i][jj] = (j < width_j && k < width_k) ? gw[(size_t)j * width_k + k] : 0.0f;
+                            }
                         wgrad_tile(wacc, G + (size_t)(jb + jl) * RS, 4, Zb + (size_t)(kb + kl) * RS, 8, RS, C * T);
 #pragma unroll
                         for (int i = 0; i < WJ; ++i) {
@@ -254,7 +261,7 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
                                 const int k = kb + kl + 8 * jj;
                                 if (j < width_j && k < width_k) {
                                     const float2 v = unpack2(wacc[i][jj]);
-                                    gw[(size_t)j * width_k + k] += v.x + v.y;
+                                    gw[(size_t)j * width_k + k] = old[i][jj] + (v.x + v.y);
                                 }
                             }
                         }
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
 #pragma unroll
                                 for (int f = 0; f < N1; ++f) s = fmaf(sf[f], sp.dir[f][net.in_coord[i]], s);
                                 s = pg_sum(s);
-                                if (jm.pg_lane == 0) atomicAdd(&sgrad[pl.g_w0[n] + u * net.n_in + i], s);
+                                if (jm.pg_lane == 0) sg[pl.g_w0[n] + u * net.n_in + i] += s;
                             }
                     }
                 }
@@ -317,14 +324,19 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
         const PjNet& net = sp.net[n];
         const int L = net.n_linear - 1;
         const int h1 = net.width[1], hL = net.width[L], hpL = pl.hp[n][L], n_out = net.width[net.n_linear];
-        for (int e = tid; e < h1 * net.n_in; e += NT_COMPUTE) gpart[net.w_off[0] + e] += sgrad[pl.g_w0[n] + e];
+        auto sgsum = [&](int idx) {
+            float v = 0.0f;
+            for (int c = 0; c < pl.sgrad_copies; ++c) v += sgrad[(size_t)c * pl.sgrad_floats + idx];
+            return v;
+        };
+        for (int e = tid; e < h1 * net.n_in; e += NT_COMPUTE) gpart[net.w_off[0] + e] += sgsum(pl.g_w0[n] + e);
         for (int hl = 0; hl < L; ++hl)
-            for (int e = tid; e < net.width[hl + 1]; e += NT_COMPUTE) gpart[net.b_off[hl] + e] += sgrad[pl.g_b[n][hl] + e];
+            for (int e = tid; e < net.width[hl + 1]; e += NT_COMPUTE) gpart[net.b_off[hl] + e] += sgsum(pl.g_b[n][hl] + e);
         for (int e = tid; e < n_out * hL; e += NT_COMPUTE) {
             const int o = e / hL, k = e - o * hL;
-            gpart[net.w_off[L] + e] += sgrad[pl.g_wl[n] + o * hpL + k];
+            gpart[net.w_off[L] + e] += sgsum(pl.g_wl[n] + o * hpL + k);
         }
-        for (int e = tid; e < n_out; e += NT_COMPUTE) gpart[net.b_off[L] + e] += sgrad[pl.g_bout[n] + e];
+        for (int e = tid; e < n_out; e += NT_COMPUTE) gpart[net.b_off[L] + e] += sgsum(pl.g_bout[n] + e);
     }
 }
 

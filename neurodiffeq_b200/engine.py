@@ -120,7 +120,6 @@ class FusedProblem:
         self.pack_buf = None
         self.workspace = None
         self._ws_points = 0
-        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.kernel_launches = 0
 
     # ---- parameters: one flat fp32 buffer, nn.Parameters become views (torch layout preserved) ----------------------
@@ -131,7 +130,10 @@ class FusedProblem:
             params += nd.parameters()
         n_theta = sum(p.numel() for p in params)
         self.theta = torch.empty(n_theta, dtype=torch.float32, device=self.device)
-        self.grad = torch.zeros(n_theta, dtype=torch.float32, device=self.device)
+        # one buffer [grad_theta | sum r^2] so that a multi-GPU step needs a single all-reduce
+        self.gradbuf = torch.zeros(n_theta + 1, dtype=torch.float32, device=self.device)
+        self.grad = self.gradbuf[:n_theta]
+        self.sumsq = self.gradbuf[n_theta:n_theta + 1]
         self.offsets = []
         off = 0
         with torch.no_grad():

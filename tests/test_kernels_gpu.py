@@ -41,6 +41,7 @@ def test_matches_oracle_ragged_sizes(key, n):
     params = get_params(nets)
     coords = workloads.sample_coords(wl, n, seed=99)
     ref = oracle_eval(key, params, coords)
+    ref["residual32"] = oracle_eval(key, params, coords, dtype=torch.float32, backward=False)["residual"]
     u, r, loss_eval, r2, loss_train, grads = run_fused(fp, coords)
     assert_parity(u, r, loss_eval, grads, ref, label=f"{key} N={n}")
     assert_parity(None, r2, loss_train, None, ref, label=f"{key} N={n} (train fwd)")

@@ -49,7 +49,9 @@ def main():
     seeds = ws[info["ws_seed"]:info["ws_seed"] + 4 * tp.n_yrows * T * n_tiles].view(np.float32).reshape(n_tiles, tp.n_yrows, T)
     for k, nd in enumerate(tp.nets):
         for h in range(1, len(nd.linears)):
-            zref = ref["z_store"][k][h - 1]  # [C, width, N]
+            zref = ref["z_store"][k][h - 1].copy()  # [C, width, N]
+            if nd.act == 0:
+                zref[0] = np.tanh(zref[0])  # K1 stores tanh(z0) in channel 0 for tanh nets
             hp = info["hp"][k][h]
             blk = zj[:, info["zj_off"][k][h]: info["zj_off"][k][h] + hp * RS].reshape(n_tiles, hp, RS)[:, :, :C * T]
             blk = blk.reshape(n_tiles, hp, C, T).transpose(2, 1, 0, 3).reshape(C, hp, n_tiles * T)[:, :nd.widths[h], :n]
