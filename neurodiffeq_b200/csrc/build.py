@@ -13,6 +13,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 LIB = os.path.join(HERE, "libpinnjet.so")
+LIB_TIMING = os.path.join(HERE, "libpinnjet_timing.so")   # diagnostic build with per-phase clock64 counters
 
 
 def _sources():
@@ -34,10 +35,11 @@ def _compile(job):
     return out, r.returncode, r.stdout + r.stderr
 
 
-def build(force=False, verbose=False, extra_flags=()):
-    if not force and up_to_date():
+def build(force=False, verbose=False, extra_flags=(), lib=None, objdir_name="build"):
+    lib = lib or LIB
+    if not force and lib == LIB and up_to_date():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, objdir_name)
     os.makedirs(objdir, exist_ok=True)
     jobs = [(os.path.join(objdir, "api.o"), os.path.join(HERE, "pinnjet_api.cu"), list(extra_flags)),
             (os.path.join(objdir, "inst_common.o"), os.path.join(HERE, "pinnjet_inst.cu"),
@@ -54,7 +56,7 @@ def build(force=False, verbose=False, extra_flags=()):
     with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         for out, log in logs:
             f.write(f"==== {os.path.basename(out)}\n{log}\n")
-    cmd = [NVCC, "-shared", "-o", LIB] + [j[0] for j in jobs] + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [NVCC, "-shared", "-o", lib] + [j[0] for j in jobs] + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
@@ -62,8 +64,15 @@ def build(force=False, verbose=False, extra_flags=()):
         for out, log in logs:
             print("====", os.path.basename(out))
             print(log)
-    return LIB
+    return lib
+
+
+def build_timing():
+    return build(force=True, extra_flags=["-DPJ_TIMING=1", "-rdc=false"], lib=LIB_TIMING, objdir_name="build_timing")
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--timing" in sys.argv:
+        print(build_timing())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -10,7 +10,8 @@ namespace pj {
 // per-scheme launchers, defined in pinnjet_inst.cu (one translation unit per jet-channel scheme)
 #define PJ_DECL(N1, N2)                                                                  \
     cudaError_t launch_k1_##N1##_##N2(const K1Args& a, int grid, int smem, cudaStream_t s); \
-    cudaError_t launch_k2_##N1##_##N2(const K2Args& a, int grid, int smem, cudaStream_t s);
+    cudaError_t launch_k2_##N1##_##N2(const K2Args& a, int grid, int smem, cudaStream_t s); \
+    int occupancy_##N1##_##N2(int which, int ntc, int smem);
 PJ_DECL(1, 0)
 PJ_DECL(1, 1)
 PJ_DECL(2, 0)
@@ -28,11 +29,12 @@ struct SchemeEntry {
     int n1, n2;
     K1Launch k1;
     K2Launch k2;
+    int (*occ)(int, int, int);
 };
 static const SchemeEntry kSchemes[] = {
-    {1, 0, launch_k1_1_0, launch_k2_1_0}, {1, 1, launch_k1_1_1, launch_k2_1_1}, {2, 0, launch_k1_2_0, launch_k2_2_0},
-    {2, 1, launch_k1_2_1, launch_k2_2_1}, {2, 2, launch_k1_2_2, launch_k2_2_2}, {3, 0, launch_k1_3_0, launch_k2_3_0},
-    {3, 3, launch_k1_3_3, launch_k2_3_3},
+    {1, 0, launch_k1_1_0, launch_k2_1_0, occupancy_1_0}, {1, 1, launch_k1_1_1, launch_k2_1_1, occupancy_1_1}, {2, 0, launch_k1_2_0, launch_k2_2_0, occupancy_2_0},
+    {2, 1, launch_k1_2_1, launch_k2_2_1, occupancy_2_1}, {2, 2, launch_k1_2_2, launch_k2_2_2, occupancy_2_2}, {3, 0, launch_k1_3_0, launch_k2_3_0, occupancy_3_0},
+    {3, 3, launch_k1_3_3, launch_k2_3_3, occupancy_3_3},
 };
 
 static thread_local char g_err[512] = "";
@@ -57,8 +59,24 @@ constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA on sm_100
 constexpr int LOSS_PART_BYTES = 4096;
 constexpr int PROG_MAX = 1024;
 
+// Weight-ring depth: keep all chunks resident if that still allows `target_occ` CTAs per SM; otherwise stream with as many
+// stages as fit (>= 2), giving up one CTA per SM at a time.  Returns -1 if nothing fits.
+static int pick_stages(int fixed_bytes, int chunks, int target_occ) {
+    if (chunks == 0) return fixed_bytes <= SMEM_LIMIT ? 1 : -1;
+    const int per_sm = 233472 - 1024;   // 228 KB per SM minus reserve
+    for (int occ = target_occ; occ >= 1; --occ) {
+        int budget = per_sm / occ - 1024;
+        if (budget > SMEM_LIMIT) budget = SMEM_LIMIT;
+        int ns = (budget - fixed_bytes) / (CHUNK_FLOATS * 4);
+        if (ns > MAX_STAGES) ns = MAX_STAGES;
+        if (ns > chunks) ns = chunks;
+        if (ns >= 2 || (ns >= 1 && ns >= chunks)) return ns;
+    }
+    return -1;
+}
+
 // Everything the kernels need to agree on.  prog_len only moves the end of the K1 shared-memory image.
-static int make_plan(const PjSpec& sp, long long N, int prog_len, Plan& pl) {
+static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int ntc_req, Plan& pl, int* occ_min) {
     memset(&pl, 0, sizeof(pl));
     if (sp.abi_version != PJ_ABI_VERSION) return fail(-1, "PjSpec.abi_version %d != %d", sp.abi_version, PJ_ABI_VERSION);
     if (sp.n_nets < 1 || sp.n_nets > PJ_MAX_NETS) return fail(-1, "n_nets=%d out of range", sp.n_nets);
@@ -96,15 +114,16 @@ static int make_plan(const PjSpec& sp, long long N, int prog_len, Plan& pl) {
     if (yrows > 32) return fail(-2, "jet table has %d rows (max 32)", yrows);
     if (hmax > 64) hmax = 128; else if (hmax > 32) hmax = 64;
     pl.hmax = hmax;
-    pl.T = NT_COMPUTE * pl.P * pl.Q / hmax;
-    if ((pl.T / pl.P) % 8 != 0 || pl.T > EPI_BATCH) return fail(-3, "internal: tile %d unsupported", pl.T);
+    pl.ntc = ntc_req;
+    if (ntc_req == 128 && hmax > 64) return fail(-3, "internal: 128-thread CTAs need hidden width <= 64");
+    pl.T = pl.ntc * pl.P * pl.Q / hmax;
+    if ((pl.T / pl.P) % 8 != 0 || pl.T > pl.ntc) return fail(-3, "internal: tile %d unsupported", pl.T);
     pl.RS = C * pl.T + ROW_PAD;
     pl.n_tiles = (int)((N + pl.T - 1) / pl.T);
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return fail(-4, "cannot query the CUDA device");
-    pl.grid = pl.n_tiles < sms ? pl.n_tiles : sms;
-    if (pl.grid > LOSS_PART_BYTES / 4) pl.grid = LOSS_PART_BYTES / 4;
+    pl.grid = pl.grid_bwd = pl.n_tiles < sms ? pl.n_tiles : sms;   // refined below once shared memory is known
 
     // ---- packed parameters ----
     int off = 0;
@@ -146,37 +165,23 @@ static int make_plan(const PjSpec& sp, long long N, int prog_len, Plan& pl) {
     pl.sgrad_floats = round_up(off, 4);
     pl.sgrad_copies = (pl.T / pl.P) / 8;
 
-    // ---- workspace ----
-    long long zt = 0;
-    for (int n = 0; n < sp.n_nets; ++n)
-        for (int h = 1; h < sp.net[n].n_linear; ++h) { pl.zj_off[n][h] = (int)zt; zt += (long long)pl.hp[n][h] * pl.RS; }
-    pl.zj_tile_floats = zt;
-    pl.ws_loss = 0;
-    pl.ws_zj = LOSS_PART_BYTES;
-    pl.ws_seed = round_up_ll(pl.ws_zj + 4ll * zt * pl.n_tiles, 256);
-    pl.ws_gpart = round_up_ll(pl.ws_seed + 4ll * sp.n_yrows * pl.T * pl.n_tiles, 256);
-    pl.ws_bytes = round_up_ll(pl.ws_gpart + 4ll * sp.n_theta * pl.grid, 256);
-
     // ---- shared memory images ----
     const int jet_bytes = hmax * pl.RS * 4;
     const int small_bytes = round_up(pl.small_floats * 4, 128);
     const int misc_bytes = 256;
     {   // K1: act | ring | small | ycache | slots | misc | prog
-        const int fixed = jet_bytes + small_bytes + sp.n_yrows * EPI_BATCH * 4 + sp.n_slots * EPI_BATCH * 4 + misc_bytes +
+        const int fixed = jet_bytes + small_bytes + sp.n_yrows * pl.ntc * 4 + sp.n_slots * pl.ntc * 4 + misc_bytes +
                           prog_len * 16;
-        int ns = (SMEM_LIMIT - fixed) / (CHUNK_FLOATS * 4);
-        if (ns > MAX_STAGES) ns = MAX_STAGES;
-        if (ns > pl.chunks_fwd) ns = pl.chunks_fwd;
-        if (pl.chunks_fwd > 0 && ns < 2 && ns < pl.chunks_fwd) return fail(-2, "forward kernel does not fit in shared memory");
-        if (ns < 1) ns = 1;
+        const int ns = pick_stages(fixed, pl.chunks_fwd, pl.ntc == 128 ? 3 : 1);
+        if (ns < 0) return fail(-2, "forward kernel does not fit in shared memory");
         pl.n_stage = ns;   // forward value; the backward value is stored in resident_bwd's companion below
         pl.resident_fwd = ns >= pl.chunks_fwd;
         int o = 0;
         pl.k1_act = o; o += jet_bytes;
         pl.k1_ring = o; o += ns * CHUNK_FLOATS * 4;
         pl.k1_small = o; o += small_bytes;
-        pl.k1_ycache = o; o += sp.n_yrows * EPI_BATCH * 4;
-        pl.k1_slots = o; o += sp.n_slots * EPI_BATCH * 4;
+        pl.k1_ycache = o; o += sp.n_yrows * pl.ntc * 4;
+        pl.k1_slots = o; o += sp.n_slots * pl.ntc * 4;
         pl.k1_misc = o; o += misc_bytes;
         pl.k1_prog = o; o += prog_len * 16;
         pl.k1_bytes = o;
@@ -185,11 +190,8 @@ static int make_plan(const PjSpec& sp, long long N, int prog_len, Plan& pl) {
         const int ybar_bytes = round_up(PJ_MAX_NETS * C * pl.T * 4, 128);
         const int sgrad_bytes = round_up(pl.sgrad_floats * pl.sgrad_copies * 4, 128);
         const int fixed = 3 * jet_bytes + small_bytes + ybar_bytes + sgrad_bytes + misc_bytes;
-        int ns = (SMEM_LIMIT - fixed) / (CHUNK_FLOATS * 4);
-        if (ns > MAX_STAGES) ns = MAX_STAGES;
-        if (ns > pl.chunks_bwd) ns = pl.chunks_bwd;
-        if (pl.chunks_bwd > 0 && ns < 2 && ns < pl.chunks_bwd) return fail(-2, "backward kernel does not fit in shared memory");
-        if (ns < 1) ns = 1;
+        const int ns = pick_stages(fixed, pl.chunks_bwd, pl.ntc == 128 ? 2 : 1);
+        if (ns < 0) return fail(-2, "backward kernel does not fit in shared memory");
         pl.resident_bwd = ns >= pl.chunks_bwd ? 1 : 0;
         pl.chunks_bwd = pl.chunks_bwd;   // (kept)
         int o = 0;
@@ -204,7 +206,43 @@ static int make_plan(const PjSpec& sp, long long N, int prog_len, Plan& pl) {
         pl.k2_bytes = o;
         pl.n_stage_bwd = ns;
     }
+    // ---- persistent grids: resident CTAs per SM x SMs, capped by the number of tiles ----
+    {
+        const SchemeEntry* e = find_scheme(sp.n1, sp.n2);
+        const int o1 = e->occ(1, pl.ntc, pl.k1_bytes), o2 = e->occ(2, pl.ntc, pl.k2_bytes);
+        if (o1 < 1 || o2 < 1) return fail(-2, "kernel does not fit on an SM (occupancy %d / %d, smem %d / %d B)", o1, o2,
+                                          pl.k1_bytes, pl.k2_bytes);
+        pl.grid = pl.n_tiles < sms * o1 ? pl.n_tiles : sms * o1;
+        pl.grid_bwd = pl.n_tiles < sms * o2 ? pl.n_tiles : sms * o2;
+        if (pl.grid > 640) pl.grid = 640;   // loss partials live in the first 2.5 KB of the workspace
+        *occ_min = o1 < o2 ? o1 : o2;
+    }
+    // ---- workspace ----
+    long long zt = 0;
+    for (int n = 0; n < sp.n_nets; ++n)
+        for (int h = 1; h < sp.net[n].n_linear; ++h) { pl.zj_off[n][h] = (int)zt; zt += (long long)pl.hp[n][h] * pl.RS; }
+    pl.zj_tile_floats = zt;
+    pl.ws_loss = 0;
+    pl.ws_zj = LOSS_PART_BYTES;
+    pl.ws_seed = round_up_ll(pl.ws_zj + 4ll * zt * pl.n_tiles, 256);
+    pl.ws_gpart = round_up_ll(pl.ws_seed + 4ll * sp.n_yrows * pl.T * pl.n_tiles, 256);
+    pl.ws_bytes = round_up_ll(pl.ws_gpart + 4ll * sp.n_theta * pl.grid_bwd, 256);
+
     return 0;
+}
+
+// Narrow networks (hidden width <= 64) run 128-thread CTAs when at least two of them fit on an SM in BOTH kernels (their
+// GEMM / activation / program phases then overlap); otherwise one 256-thread CTA per SM.
+static int make_plan(const PjSpec& sp, long long N, int prog_len, Plan& pl) {
+    int occ = 0, hmax = 0;
+    for (int n = 0; n < sp.n_nets && n < PJ_MAX_NETS; ++n)
+        for (int h = 1; h < sp.net[n].n_linear && h <= PJ_MAX_LINEAR; ++h)
+            if (sp.net[n].width[h] > hmax) hmax = sp.net[n].width[h];
+    if (hmax <= 64) {
+        const int rc = make_plan_ntc(sp, N, prog_len, 128, pl, &occ);
+        if (rc == 0 && occ >= 2) return 0;
+    }
+    return make_plan_ntc(sp, N, prog_len, 256, pl, &occ);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -354,6 +392,7 @@ static int run_k1(const PjSpec* spec, const int32_t* prog, int32_t prog_len, con
     a.r_out = r_out;
     char* w = static_cast<char*>(ws);
     a.loss_part = reinterpret_cast<float*>(w + a.plan.ws_loss);
+    a.dbg = a.loss_part + 640;   // tail of the 4 KB loss-partial block (only written by PJ_TIMING builds)
     a.zj = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_zj) : nullptr;
     a.seeds = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_seed) : nullptr;
     const SchemeEntry* e = find_scheme(spec->n1, spec->n2);
@@ -394,9 +433,10 @@ int pj_backward(const PjSpec* spec, const float* const* coords, int64_t n_points
     a.zj = reinterpret_cast<const float*>(w + a.plan.ws_zj);
     a.seeds = reinterpret_cast<const float*>(w + a.plan.ws_seed);
     a.gpart = reinterpret_cast<float*>(w + a.plan.ws_gpart);
+    a.dbg = reinterpret_cast<float*>(w + a.plan.ws_loss) + 640;
     const SchemeEntry* e = find_scheme(spec->n1, spec->n2);
-    if (int rc = check_cuda(e->k2(a, a.plan.grid, a.plan.k2_bytes, (cudaStream_t)stream), "backward launch")) return rc;
-    return check_cuda(launch_reduce(a.gpart, a.plan.grid, spec->n_theta, grad_theta, (cudaStream_t)stream), "reduce launch");
+    if (int rc = check_cuda(e->k2(a, a.plan.grid_bwd, a.plan.k2_bytes, (cudaStream_t)stream), "backward launch")) return rc;
+    return check_cuda(launch_reduce(a.gpart, a.plan.grid_bwd, spec->n_theta, grad_theta, (cudaStream_t)stream), "reduce launch");
 }
 
 }  // extern "C"

@@ -18,10 +18,9 @@
 
 namespace pj {
 
-constexpr int NT_COMPUTE = 256;          // compute threads (8 warps)
-constexpr int NT_TOTAL = 288;            // + producer warp
-constexpr int N_CWARPS = NT_COMPUTE / 32;
-constexpr int EPI_BATCH = 256;           // points per residual-program batch (one per compute thread)
+// CTA shape: NTC compute threads (128 or 256: template parameter of the kernels) + one producer warp.  Narrow networks
+// (hidden width <= 64) use 128-thread CTAs so that several CTAs share an SM and their GEMM / activation / program phases
+// overlap; the residual program is batched over NTC points (one per compute thread).
 constexpr int CHUNK_FLOATS = 4096;       // weight chunk = 16 KB
 constexpr int MAX_STAGES = 8;
 constexpr int ROW_PAD = 4;               // jet rows are C*T + 4 floats: conflict-free row-strided float4 loads
@@ -36,7 +35,7 @@ enum : int {
 // Everything derived from (spec, N): identical on host and device, computed by make_plan() in pinnjet_api.cu.
 struct Plan {
     int T, P, Q, C, RS;                  // tile points, thread tile, channels, jet row stride (floats)
-    int n_tiles, grid, hmax;
+    int n_tiles, grid, grid_bwd, hmax, ntc;   // grid: K1 CTAs (= loss partials), grid_bwd: K2 CTAs (= gradient partials)
     int n_stage, n_stage_bwd, resident_fwd, resident_bwd, chunks_fwd, chunks_bwd;   // n_stage: forward ring
     int hp[PJ_MAX_NETS][PJ_MAX_LINEAR + 1];   // padded widths (hidden -> multiple of 32; input/output unpadded)
     // ---- packed parameter copy (float offsets) ----
@@ -78,6 +77,7 @@ struct K1Args {
     float* zj;
     float* seeds;
     float* loss_part;
+    float* dbg;                          // diagnostic builds only (PJ_TIMING): phase cycle counters
 };
 
 struct K2Args {
@@ -89,6 +89,7 @@ struct K2Args {
     const float* zj;
     const float* seeds;
     float* gpart;
+    float* dbg;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -128,8 +129,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// barrier among the 256 compute threads only (the producer warp never joins)
-__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// barrier among the compute threads only (the producer warp never joins)
+template <int NTC>
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
 
 // packed pair of fp32 in one 64-bit register pair: the operand type of fma.rn.f32x2 (SASS FFMA2)
 typedef unsigned long long f2;
@@ -276,6 +278,25 @@ __device__ __forceinline__ float pick(const f2 (&v)[P / 2], int p) {
     const float2 t = unpack2(v[p >> 1]);
     return (p & 1) ? t.y : t.x;
 }
+
+// ---- optional phase timing (diagnostic build only: -DPJ_TIMING=1 -> libpinnjet_timing.so; never in the product) --------
+#ifdef PJ_TIMING
+#define PJ_T_DECL unsigned long long pj_t_last = clock64(), pj_t_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PJ_T_MARK(slot)                              \
+    {                                                \
+        const unsigned long long now_ = clock64();   \
+        pj_t_acc[slot] += now_ - pj_t_last;          \
+        pj_t_last = now_;                            \
+    }
+#define PJ_T_FLUSH(base)                                                           \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                     \
+        for (int i_ = 0; i_ < 12; ++i_) A.dbg[(base) + i_] = (float)pj_t_acc[i_];     \
+    }
+#else
+#define PJ_T_DECL
+#define PJ_T_MARK(slot)
+#define PJ_T_FLUSH(base)
+#endif
 
 // thread -> (point group, unit group) mapping shared by K1 and K2: a warp covers 8 point groups x 4 unit groups
 struct JobMap {

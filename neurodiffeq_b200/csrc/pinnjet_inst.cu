@@ -56,29 +56,68 @@ cudaError_t launch_loss_finalize(const float* part, int n_parts, float* out, cud
 constexpr int kC = 1 + PJ_N1 + PJ_N2;
 constexpr int kP = (kC <= 2) ? 4 : 2;   // must match make_plan() in pinnjet_api.cu
 constexpr int kQ = 4;
+// CTAs per SM the register allocation is tuned for (shared memory may allow fewer): 128-thread CTAs share an SM
+constexpr int kMinB1_128 = 3, kMinB2_128 = 2;
+
+template <typename K>
+static cudaError_t configure(K kern, int& configured) {
+    if (configured) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) configured = 1;
+    return e;
+}
 
 cudaError_t PJ_NAME(launch_k1_, PJ_N1, PJ_N2)(const K1Args& a, int grid, int smem, cudaStream_t s) {
-    auto kern = k1_forward_kernel<kP, kQ, PJ_N1, PJ_N2>;
-    static int configured = -1;
-    if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        if (e != cudaSuccess) return e;
-        configured = 232448;
+    static int c128 = 0, c256 = 0;
+    if (a.plan.ntc == 128) {
+        auto kern = k1_forward_kernel<128, kMinB1_128, kP, kQ, PJ_N1, PJ_N2>;
+        if (cudaError_t e = configure(kern, c128)) return e;
+        kern<<<grid, 160, smem, s>>>(a);
+    } else {
+        auto kern = k1_forward_kernel<256, 1, kP, kQ, PJ_N1, PJ_N2>;
+        if (cudaError_t e = configure(kern, c256)) return e;
+        kern<<<grid, 288, smem, s>>>(a);
     }
-    kern<<<grid, NT_TOTAL, smem, s>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t PJ_NAME(launch_k2_, PJ_N1, PJ_N2)(const K2Args& a, int grid, int smem, cudaStream_t s) {
-    auto kern = k2_backward_kernel<kP, kQ, PJ_N1, PJ_N2>;
-    static int configured = -1;
-    if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        if (e != cudaSuccess) return e;
-        configured = 232448;
+    static int c128 = 0, c256 = 0;
+    if (a.plan.ntc == 128) {
+        auto kern = k2_backward_kernel<128, kMinB2_128, kP, kQ, PJ_N1, PJ_N2>;
+        if (cudaError_t e = configure(kern, c128)) return e;
+        kern<<<grid, 160, smem, s>>>(a);
+    } else {
+        auto kern = k2_backward_kernel<256, 1, kP, kQ, PJ_N1, PJ_N2>;
+        if (cudaError_t e = configure(kern, c256)) return e;
+        kern<<<grid, 288, smem, s>>>(a);
     }
-    kern<<<grid, NT_TOTAL, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+// resident CTAs per SM for (kernel, ntc, dynamic smem): which = 1 -> K1, 2 -> K2
+int PJ_NAME(occupancy_, PJ_N1, PJ_N2)(int which, int ntc, int smem) {
+    int n = 0;
+    cudaError_t e;
+    static int c[4] = {0, 0, 0, 0};
+    if (which == 1 && ntc == 128) {
+        auto kern = k1_forward_kernel<128, kMinB1_128, kP, kQ, PJ_N1, PJ_N2>;
+        configure(kern, c[0]);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 160, smem);
+    } else if (which == 1) {
+        auto kern = k1_forward_kernel<256, 1, kP, kQ, PJ_N1, PJ_N2>;
+        configure(kern, c[1]);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 288, smem);
+    } else if (ntc == 128) {
+        auto kern = k2_backward_kernel<128, kMinB2_128, kP, kQ, PJ_N1, PJ_N2>;
+        configure(kern, c[2]);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 160, smem);
+    } else {
+        auto kern = k2_backward_kernel<256, 1, kP, kQ, PJ_N1, PJ_N2>;
+        configure(kern, c[3]);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 288, smem);
+    }
+    return e == cudaSuccess ? n : -1;
 }
 
 #endif

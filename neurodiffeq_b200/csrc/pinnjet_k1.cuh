@@ -68,9 +68,10 @@ struct RingCursor {
     }
 };
 
-template <int P, int Q, int N1, int N2>
-__global__ void __launch_bounds__(NT_TOTAL, 1) k1_forward_kernel(const __grid_constant__ K1Args A) {
+template <int NTC, int MINB, int P, int Q, int N1, int N2>
+__global__ void __launch_bounds__(NTC + 32, MINB) k1_forward_kernel(const __grid_constant__ K1Args A) {
     constexpr int C = 1 + N1 + N2;
+    constexpr int NT_COMPUTE = NTC, NT_TOTAL = NTC + 32, N_CWARPS = NTC / 32, EPI_BATCH = NTC;
     extern __shared__ __align__(128) unsigned char smem[];
     const PjSpec& sp = A.spec;
     const Plan& pl = A.plan;
@@ -112,6 +113,8 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k1_forward_kernel(const __grid_co
     const bool train = A.mode == 1;
     float my_sumsq = 0.0f;
     int batch_n = 0, batch_first_iter = 0;
+    PJ_T_DECL   // slots: 0 setup, 1 layer0, 2 gemm, 3 barrier-after-gemm, 4 epilogue, 5 output layer, 6 program
+    PJ_T_MARK(0)
 
     for (int iter = 0; iter < my_tiles; ++iter) {
         const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
@@ -189,7 +192,8 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k1_forward_kernel(const __grid_co
                     }
                 }
             }
-            bar_compute();
+            bar_compute<NTC>();
+            PJ_T_MARK(1)
 
             // ---------------- hidden -> hidden Linears l = 1..L-1 ----------------
             for (int l = 1; l < L; ++l) {
@@ -208,7 +212,9 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k1_forward_kernel(const __grid_co
                     if (valid) gemm_rows<P, Q, C>(acc, act + r0 * RS + p0, RS, T, chunk + u0, NO, min(rpc, K - r0));
                     cur.release(lane);
                 }
-                bar_compute();   // every read of the previous layer's jets is done -> overwrite in place
+                PJ_T_MARK(2)
+                bar_compute<NTC>();   // every read of the previous layer's jets is done -> overwrite in place
+                PJ_T_MARK(3)
                 if (valid) {
                     const float* bl = small + pl.s_b[n][l];
                     float* zrow = train ? zj_tile + pl.zj_off[n][l + 1] : nullptr;
@@ -257,7 +263,8 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k1_forward_kernel(const __grid_co
                         }
                     }
                 }
-                bar_compute();
+                bar_compute<NTC>();
+                PJ_T_MARK(4)
             }
 
             // ---------------- last Linear: hidden L -> raw outputs, all channels, into the batch jet table -------------
@@ -274,7 +281,8 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k1_forward_kernel(const __grid_co
                     ycache[(net.yrow0 + row) * EPI_BATCH + batch_n + pt] = s;
                 }
             }
-            bar_compute();
+            bar_compute<NTC>();
+            PJ_T_MARK(5)
         }
 
         // ---------------- residual program over the collected batch ----------------
@@ -288,19 +296,21 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k1_forward_kernel(const __grid_co
                 float* seed_tile = train ? A.seeds + btile * ((long long)sp.n_yrows * T) + pt : nullptr;
                 if (gidx < A.N) {
                     ProgIO io{A.coords, gidx, A.N, ycache + tid, A.rbar, A.loss_scale, A.u_out, A.r_out, seed_tile, T};
-                    my_sumsq += run_program(prog_s, A.prog_len, slots + tid, io);
+                    my_sumsq += run_program<EPI_BATCH>(prog_s, A.prog_len, slots + tid, io);
                 } else if (train) {
                     for (int r = 0; r < sp.n_yrows; ++r) seed_tile[r * T] = 0.0f;   // padded points: zero adjoint
                 }
             }
             batch_n = 0;
-            bar_compute();
+            bar_compute<NTC>();
+            PJ_T_MARK(6)
         }
     }
+    PJ_T_FLUSH(0)
 
     my_sumsq = warp_sum(my_sumsq);
     if (lane == 0) red[warp] = my_sumsq;
-    bar_compute();
+    bar_compute<NTC>();
     if (tid == 0) {
         float s = 0.0f;
         for (int w = 0; w < N_CWARPS; ++w) s += red[w];

@@ -40,9 +40,10 @@ __device__ __forceinline__ void wgrad_tile(f2 (&acc)[WJ][WK], const float* __res
     }
 }
 
-template <int P, int Q, int N1, int N2>
-__global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_constant__ K2Args A) {
+template <int NTC, int MINB, int P, int Q, int N1, int N2>
+__global__ void __launch_bounds__(NTC + 32, MINB) k2_backward_kernel(const __grid_constant__ K2Args A) {
     constexpr int C = 1 + N1 + N2;
+    constexpr int NT_COMPUTE = NTC, NT_TOTAL = NTC + 32, N_CWARPS = NTC / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     const PjSpec& sp = A.spec;
     const Plan& pl = A.plan;
@@ -88,6 +89,8 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
     uint32_t zphase = 0;
     // lane mapping of the weight-gradient GEMM: 8 k-lanes x 4 j-lanes per warp
     const int kl = lane & 7, jl = lane >> 3;
+    PJ_T_DECL   // slots: 0 setup, 1 seeds+z wait, 2 last-linear stage, 3 adjoint gemm, 4 z wait, 5 reverse act, 6 wgrad, 7 layer0
+    PJ_T_MARK(0)
 
     for (int iter = 0; iter < my_tiles; ++iter) {
         const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
@@ -111,9 +114,10 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
                 tma_bulk_g2s(Zb, zj_tile + pl.zj_off[n][L], bytes, zfull);
             }
             for (int e = tid; e < n_out * C * T; e += NT_COMPUTE) ybar[e] = __ldg(seed_tile + net.yrow0 * T + e);
-            bar_compute();
+            bar_compute<NTC>();
             mbar_wait(zfull, zphase);
             zphase ^= 1u;
+            PJ_T_MARK(1)
 
             // (1) last Linear: grads of W_out, b_out; adjoint of hidden-L a-jets; reverse activation -> G = z_bar_L
             {
@@ -171,7 +175,8 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
                     sgrad[pl.g_bout[n] + tid] += s;
                 }
             }
-            bar_compute();
+            bar_compute<NTC>();
+            PJ_T_MARK(2)
 
             // (2) hidden layers h = L .. 2: Linear l = h-1 maps hidden h-1 -> hidden h
             for (int h = L; h >= 2; --h) {
@@ -198,8 +203,10 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
                     if (valid) gemm_rows<P, Q, C>(acc, G + r0 * RS + p0, RS, T, chunk + u0, HK, min(rpc, HJ - r0));
                     cur.release(lane);
                 }
+                PJ_T_MARK(3)
                 mbar_wait(zfull, zphase);
                 zphase ^= 1u;
+                PJ_T_MARK(4)
                 // (2b) reverse activation of hidden h-1: Zb z-jets -> a-jets (in place), G2 <- z_bar_{h-1}
                 if (valid) {
 #pragma unroll
@@ -234,7 +241,8 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
                         if (jm.pg_lane == 0) sg[pl.g_b[n][h - 2] + u] += gb;
                     }
                 }
-                bar_compute();
+                bar_compute<NTC>();
+                PJ_T_MARK(5)
                 // (2c) W_l gradient: out[j][k] += sum_{c,pt} G[j][c,pt] * Zb[k][c,pt]
                 {
                     const int width_j = net.width[h], width_k = net.width[h - 1];   // unpadded
@@ -267,7 +275,8 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
                         }
                     }
                 }
-                bar_compute();
+                bar_compute<NTC>();
+                PJ_T_MARK(6)
                 float* t = G;
                 G = G2;
                 G2 = t;
@@ -314,12 +323,14 @@ __global__ void __launch_bounds__(NT_TOTAL, 1) k2_backward_kernel(const __grid_c
                     }
                 }
             }
-            bar_compute();
+            bar_compute<NTC>();
+            PJ_T_MARK(7)
         }
     }
+    PJ_T_FLUSH(16)
 
     // flush the shared-memory gradient accumulators into this CTA's partial (padded units are dropped)
-    bar_compute();
+    bar_compute<NTC>();
     for (int n = 0; n < sp.n_nets; ++n) {
         const PjNet& net = sp.net[n];
         const int L = net.n_linear - 1;

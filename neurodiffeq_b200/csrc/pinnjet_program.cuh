@@ -23,6 +23,7 @@ struct ProgIO {
 };
 
 // returns sum of squared residuals of this point
+template <int EPI_BATCH>
 __device__ __forceinline__ float run_program(const int4* __restrict__ prog, int len, float* __restrict__ slot,
                                              const ProgIO& io) {
     float sumsq = 0.0f;

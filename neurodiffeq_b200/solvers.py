@@ -1,0 +1,557 @@
+"""Solver front-ends: the reference's ``Solver1D / Solver2D / SolverSpherical / BundleSolver1D`` ``.fit()`` loop
+(neurodiffeq/solvers.py:35-646, 761-974, 1020-1181, 1189-1419, 1427-1593) with the per-batch closure
+(solvers.py:369-395) replaced by the fused CUDA engine.
+
+What stays like the reference: constructor keywords, ``fit(max_epochs, callbacks=(), tqdm_file=...)``,
+``metrics_history`` keys, ``nets`` / ``conditions`` / ``optimizer`` / ``generator`` / ``n_batches`` attributes,
+``global_epoch`` / ``local_epoch`` / ``_stop_training`` / ``lowest_loss`` / ``best_nets``, ``get_solution()`` and
+``get_residuals()``; gradients accumulate over the batches of an epoch and ONE optimizer step follows
+(solvers.py:360-362, 417-419); validation runs the residual path without a backward pass (:406-407).
+
+What changes: points are sampled on the host, copied to the GPU as float32 SoA vectors, and every batch is
+K0 pack -> K1 -> K2 (-> NCCL all-reduce when ``torch.distributed`` is initialised and ``data_parallel=True``); the loss is read
+back ONCE per epoch instead of ``.item()`` per batch (:394); the best parameters are kept as a flat device copy
+instead of ``deepcopy(nets)`` per improvement (:441).  Unsupported features raise instead of silently falling back.
+"""
+import sys
+import warnings
+from copy import deepcopy
+from inspect import signature
+from itertools import chain
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .conditions import BaseCondition
+from .engine import FusedProblem
+from .generators import Generator1D, Generator2D, GeneratorSpherical, SamplerGenerator
+from .networks import FCNN
+from .parallel import shard_bounds
+
+
+def _requires_closure(optimizer):
+    # reference solvers.py:22-32: optimizers whose step() needs a closure (LBFGS)
+    return isinstance(optimizer, torch.optim.LBFGS)
+
+
+def _unique(params):
+    seen, out = set(), []
+    for p in params:
+        if id(p) not in seen:
+            seen.add(id(p))
+            out.append(p)
+    return out
+
+
+class BaseSolution:
+    """Callable solution ``u(*coords)`` evaluated by the forward kernel (reference solvers.py:650-720)."""
+
+    def __init__(self, nets, conditions, n_coords, coords_for_condition=None):
+        if nets is None:
+            raise RuntimeError("The nets cannot be None, check if you disabled validation "
+                               "and used `best`=True with `get_solution` / `get_residual`")
+        self.nets = [nets] * len(conditions) if isinstance(nets, nn.Module) else nets
+        self.conditions = conditions
+        self._n_coords = n_coords
+        self._cfc = coords_for_condition
+        self._problem = None
+
+    def _fused(self):
+        if self._problem is None:
+            self._problem = FusedProblem(self.nets, self.conditions, None, self._n_coords, self._cfc)
+        return self._problem
+
+    def __call__(self, *coords, to_numpy=False, no_reshape=False):
+        if isinstance(to_numpy, str):  # legacy `as_type`
+            if to_numpy in ("tf", "torch"):
+                to_numpy = False
+            elif to_numpy == "np":
+                to_numpy = True
+            else:
+                raise ValueError(f"Unrecognized `as_type` option: '{to_numpy}'")
+        coords = [c if isinstance(c, torch.Tensor) else torch.as_tensor(np.asarray(c)) for c in coords]
+        shape = coords[0].shape
+        fp = self._fused()
+        u, _, _ = fp.forward([c.reshape(-1) for c in coords], want_u=True, want_residual=False)
+        us = [u[k].reshape(-1, 1) if no_reshape else u[k].reshape(shape) for k in range(u.shape[0])]
+        if to_numpy:
+            us = [x.detach().cpu().numpy() for x in us]
+        return us if len(self.nets) > 1 else us[0]
+
+
+class BaseSolver:
+    """Fused counterpart of ``neurodiffeq.solvers.BaseSolver``."""
+
+    N_COORDS = None  # set by subclasses that know it a priori
+
+    def __init__(self, diff_eqs, conditions, nets=None, train_generator=None, valid_generator=None,
+                 analytic_solutions=None, optimizer=None, loss_fn=None, n_batches_train=1, n_batches_valid=4,
+                 metrics=None, n_input_units=None, n_output_units=None, shuffle=None, batch_size=None,
+                 device=None, data_parallel=True, **legacy):
+        if "criterion" in legacy:
+            loss_fn = legacy.pop("criterion")
+        if legacy:
+            raise TypeError(f"unexpected keyword arguments {list(legacy)}")
+        if shuffle:
+            warnings.warn("param `shuffle` is deprecated and ignored; shuffling should be performed by generators",
+                          FutureWarning)
+        if batch_size is not None:
+            warnings.warn("param `batch_size` is deprecated and ignored; specify n_batches_train and n_batches_valid",
+                          FutureWarning)
+        if analytic_solutions:
+            raise NotImplementedError("`analytic_solutions` is deprecated in the reference; pass a `metrics` dict")
+        if type(self).additional_loss is not BaseSolver.additional_loss:
+            raise NotImplementedError("overriding `additional_loss` is not supported by the fused solvers yet")
+        self.diff_eqs = diff_eqs
+        self.conditions = conditions
+        self.n_funcs = len(conditions)
+        if nets is None:
+            nets = [FCNN(n_input_units=n_input_units, n_output_units=n_output_units, hidden_units=(32, 32),
+                         actv=nn.Tanh) for _ in range(self.n_funcs)]
+        self.nets = nets
+        if train_generator is None:
+            raise ValueError("train_generator must be specified")
+        if valid_generator is None:
+            raise ValueError("valid_generator must be specified")
+        self.metrics_fn = metrics if metrics else {}
+        self.metrics_history = {"train_loss": [], "valid_loss": []}
+        self.metrics_history.update({"train__" + name: [] for name in self.metrics_fn})
+        self.metrics_history.update({"valid__" + name: [] for name in self.metrics_fn})
+        self.generator = {"train": SamplerGenerator(train_generator), "valid": SamplerGenerator(valid_generator)}
+        self.n_batches = {"train": n_batches_train, "valid": n_batches_valid}
+        self._batch = {"train": None, "valid": None}
+
+        # ---- the fused engine: trace once, put the parameters on the device ----
+        n_coords = n_input_units if self.N_COORDS is None else self.N_COORDS
+        if n_coords is None:
+            n_coords = len(self.generator["train"].get_examples())
+        self.n_coords = n_coords
+        self.problem = FusedProblem(self.nets, self.conditions, self._traced_diff_eqs, n_coords,
+                                    coords_for_condition=self._coords_for_condition, device=device)
+        self.device = self.problem.device
+
+        self.optimizer = optimizer if optimizer else torch.optim.Adam(
+            _unique(chain.from_iterable(n.parameters() for n in self.nets)))
+        if _requires_closure(self.optimizer):
+            raise NotImplementedError("closure-based optimizers (LBFGS, reference solvers.py:398-400) are not "
+                                      "supported by the fused solvers yet")
+        self._set_loss_fn(loss_fn)
+        self.best_nets_theta = None
+        self.lowest_loss = None
+        self.local_epoch = 0
+        self._max_local_epoch = 0
+        self._stop_training = False
+        self._phase = None
+        self._dist = None
+        if data_parallel and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            self._dist = torch.distributed
+
+    # ---- hooks for subclasses -----------------------------------------------------------------------------------------
+    def _traced_diff_eqs(self, *variables):
+        return self.diff_eqs(*variables)
+
+    def _coords_for_condition(self, k, cond, coords):
+        return tuple(coords)
+
+    def additional_loss(self, residual, funcs, coords):
+        return 0.0
+
+    def _set_loss_fn(self, criterion):
+        # None / 'l2' / nn.MSELoss: the fused mean-squared residual (reference solvers.py:216-226, losses.py:10-12).
+        # Any other callable (residual, funcs, coords) -> scalar is differentiated by autograd w.r.t. the residual
+        # only; dL/dr is then handed to the kernels (funcs / coords are passed detached).
+        self._custom_loss = None
+        if criterion is None or (isinstance(criterion, str) and criterion.lower() == "l2") \
+                or isinstance(criterion, nn.MSELoss):
+            self.loss_fn = lambda r, f, x: (r ** 2).mean()
+        elif isinstance(criterion, nn.modules.loss._Loss):
+            self.loss_fn = lambda r, f, x: criterion(r, torch.zeros_like(r))
+            self._custom_loss = self.loss_fn
+        elif isinstance(criterion, str):
+            raise NotImplementedError(f"loss '{criterion}' of neurodiffeq.losses is not available in the fused solvers "
+                                      f"(implemented: 'l2'); pass a callable (residual, funcs, coords) -> scalar")
+        elif callable(criterion):
+            self.loss_fn = criterion
+            self._custom_loss = criterion
+        else:
+            raise TypeError(f"Unknown type of criterion {type(criterion)}")
+
+    @property
+    def global_epoch(self):
+        return len(self.metrics_history["train_loss"])
+
+    @property
+    def batch(self):
+        return self._batch
+
+    @property
+    def best_nets(self):
+        """Networks with the lowest loss so far (materialised on demand from the flat device copy)."""
+        if self.best_nets_theta is None:
+            return None
+        live = self.problem.theta.clone()
+        self.problem.theta.copy_(self.best_nets_theta)
+        nets = deepcopy(self.nets)
+        self.problem.theta.copy_(live)
+        return nets
+
+    def compute_func_val(self, net, cond, *coordinates):
+        return cond.enforce(net, *coordinates)
+
+    # ---- batches ------------------------------------------------------------------------------------------------------
+    def _generate_batch(self, key):
+        self._phase = key
+        cols = self.generator[key].get_examples()
+        dev = [c.detach().reshape(-1).to(torch.float32).contiguous() for c in cols]
+        if any(c.device != self.device for c in dev):
+            dev = [c.pin_memory().to(self.device, non_blocking=True) if c.device.type == "cpu" else c.to(self.device)
+                   for c in dev]
+        if self._dist is not None:  # every rank samples the same batch (same seed) and keeps its slice
+            w, r = self._dist.get_world_size(), self._dist.get_rank()
+            n = dev[0].numel()
+            lo, hi = shard_bounds(n, r, w)
+            self._n_global = n
+            dev = [c[lo:hi].contiguous() for c in dev]
+        else:
+            self._n_global = dev[0].numel()
+        self._batch[key] = [c.reshape(-1, 1) for c in dev]
+        return dev
+
+    def _update_history(self, value, metric_type, key):
+        self._phase = key
+        if metric_type == "loss":
+            self.metrics_history[f"{key}_{metric_type}"].append(value)
+        elif metric_type in self.metrics_fn:
+            self.metrics_history[f"{key}__{metric_type}"].append(value)
+        else:
+            raise KeyError(f"metric '{metric_type}' not specified")
+
+    def _do_optimizer_step(self, closure=None):
+        self.optimizer.step(closure=closure)
+
+    def _eval_metrics(self, coords, acc):
+        if not self.metrics_fn:
+            return
+        u, _, _ = self.problem.forward(coords, want_u=True, want_residual=False, repack=False)
+        funcs = [u[k].reshape(-1, 1) for k in range(u.shape[0])]
+        cols = [c.reshape(-1, 1) for c in coords]
+        for name, fn in self.metrics_fn.items():
+            acc[name] += float(fn(*funcs, *cols).item())
+
+    def _run_epoch(self, key):
+        if self.n_batches[key] <= 0:
+            return
+        self._phase = key
+        fp = self.problem
+        if not fp.parameters_linked():
+            fp.relink()
+        metric_values = {name: 0.0 for name in self.metrics_fn}
+        n_b = self.n_batches[key]
+        loss_acc = torch.zeros(1, dtype=torch.float32, device=self.device)
+        if key == "train":
+            fp.gradbuf.zero_()          # optimizer.zero_grad(): the kernels accumulate into p.grad views
+        fp.pack()                       # parameters changed at the last optimizer step
+        for _ in range(n_b):
+            coords = self._generate_batch(key)
+            denom = float(self._n_global * fp.n_eq)          # loss of a batch = mean over its N_global * n_eq entries
+            cols = [c.reshape(-1, 1) for c in coords]
+            if self._custom_loss is None:
+                fp.sumsq.zero_()
+                if key == "train":   # gradients of the batches ADD UP (no averaging), like repeated loss.backward()
+                    fp.residual_grad(coords, n_global=self._n_global, sumsq_out=fp.sumsq, repack=False)
+                else:
+                    fp.forward(coords, want_u=False, want_residual=False, want_sumsq=True, repack=False)
+                loss_acc += fp.sumsq / denom
+            else:
+                u, r, _ = fp.forward(coords, want_u=True, want_residual=True, repack=False)
+                res = r.t().contiguous().requires_grad_(key == "train")      # (N, n_eq) like torch.cat(residuals, 1)
+                funcs = [u[k].reshape(-1, 1) for k in range(u.shape[0])]
+                loss = self._custom_loss(res, funcs, cols) + self.additional_loss(res, funcs, cols)
+                if key == "train":
+                    loss.backward()                                          # only to get dL/dr on the tiny leaf
+                    fp.residual_grad(coords, rbar=res.grad.t().contiguous(), sumsq_out=fp.sumsq, repack=False)
+                loss_acc += loss.detach().reshape(1).to(torch.float32)
+            self._eval_metrics(coords, metric_values)
+        if self._dist is not None:   # one collective per epoch phase: [grad | loss] summed over the ranks
+            fp.sumsq.copy_(loss_acc)
+            if key == "train":
+                self._dist.all_reduce(fp.gradbuf)
+            else:
+                self._dist.all_reduce(fp.sumsq)
+            loss_acc = fp.sumsq.clone()
+            if self._custom_loss is not None:
+                loss_acc /= self._dist.get_world_size()
+        epoch_loss = float(loss_acc.item()) / n_b        # mean of the batch losses (reference solvers.py:410)
+        self._update_history(epoch_loss, "loss", key)
+        if key == "valid" or self.n_batches["valid"] == 0:
+            self._update_best(key)
+        if key == "train":
+            self._do_optimizer_step()
+        for name in self.metrics_fn:
+            self._update_history(metric_values[name] / n_b, name, key)
+
+    def run_train_epoch(self):
+        self._run_epoch("train")
+
+    def run_valid_epoch(self):
+        self._run_epoch("valid")
+
+    def _update_best(self, key):
+        current = self.metrics_history[key + "_loss"][-1]
+        if self.lowest_loss is None or current < self.lowest_loss:
+            self.lowest_loss = current
+            if self.best_nets_theta is None:
+                self.best_nets_theta = self.problem.theta.clone()
+            else:
+                self.best_nets_theta.copy_(self.problem.theta)
+
+    def fit(self, max_epochs, callbacks=(), tqdm_file=sys.stderr, **kwargs):
+        self._stop_training = False
+        self._max_local_epoch = max_epochs
+        if kwargs:
+            raise ValueError(f"Unknown keyword argument(s): {list(kwargs.keys())}")
+        loop = range(max_epochs)
+        if tqdm_file is not None:
+            try:
+                from tqdm.auto import tqdm
+                loop = tqdm(loop, desc="Training Progress", file=tqdm_file, dynamic_ncols=True)
+            except ImportError:
+                pass
+        for local_epoch in loop:
+            if self._stop_training:
+                break
+            self.local_epoch = local_epoch + 1
+            self.run_train_epoch()
+            self.run_valid_epoch()
+            for cb in callbacks:
+                cb(self)
+
+    # ---- solutions / residuals ----------------------------------------------------------------------------------------
+    def _solution_class(self):
+        return BaseSolution
+
+    def get_solution(self, copy=True, best=True):
+        nets = self.best_nets if best else self.nets
+        if nets is None:
+            raise RuntimeError("The nets cannot be None, check if you disabled validation "
+                               "and used `best`=True with `get_solution` / `get_residual`")
+        conditions = self.conditions
+        if copy:
+            if not best:
+                nets = deepcopy(nets)
+            conditions = deepcopy(conditions)
+        elif best:
+            warnings.warn("copy=False with best=True returns a copy of the best networks", RuntimeWarning)
+        return self._solution_class()(nets, conditions, self.n_coords, self._coords_for_condition)
+
+    def get_residuals(self, *coords, to_numpy=False, best=True, no_reshape=False):
+        coords = [c if isinstance(c, torch.Tensor) else torch.as_tensor(np.asarray(c)) for c in coords]
+        shape = coords[0].shape
+        fp = self.problem
+        if best and self.best_nets_theta is not None:
+            live = fp.theta.clone()
+            fp.theta.copy_(self.best_nets_theta)
+            _, r, _ = fp.forward([c.reshape(-1) for c in coords], want_u=False, want_residual=True)
+            fp.theta.copy_(live)
+            fp.pack()
+        else:
+            _, r, _ = fp.forward([c.reshape(-1) for c in coords], want_u=False, want_residual=True)
+        rs = [r[e].reshape(-1, 1) if no_reshape else r[e].reshape(shape) for e in range(r.shape[0])]
+        if to_numpy:
+            rs = [x.detach().cpu().numpy() for x in rs]
+        return rs if len(rs) > 1 else rs[0]
+
+    def _get_internal_variables(self):
+        return {
+            "metrics": self.metrics_fn, "n_batches": self.n_batches, "best_nets": self.best_nets,
+            "criterion": self.loss_fn, "loss_fn": self.loss_fn, "conditions": self.conditions,
+            "global_epoch": self.global_epoch, "lowest_loss": self.lowest_loss, "n_funcs": self.n_funcs,
+            "nets": self.nets, "optimizer": self.optimizer, "diff_eqs": self.diff_eqs, "generator": self.generator,
+            "train_generator": self.generator["train"], "valid_generator": self.generator["valid"],
+        }
+
+    def get_internals(self, var_names=None, return_type="list"):
+        available = self._get_internal_variables()
+        if var_names == "all" or var_names is None:
+            return available
+        if isinstance(var_names, str):
+            return available[var_names]
+        if return_type == "list":
+            return [available[name] for name in var_names]
+        if return_type == "dict":
+            return {name: available[name] for name in var_names}
+        raise ValueError(f"unrecognized return_type = {return_type}")
+
+
+class GenericSolver(BaseSolver):
+    pass
+
+
+class Solution1D(BaseSolution):
+    pass
+
+
+class Solution2D(BaseSolution):
+    pass
+
+
+class SolutionSpherical(BaseSolution):
+    pass
+
+
+class BundleSolution1D(BaseSolution):
+    pass
+
+
+def _need_bounds(lo, hi, names, train_generator, valid_generator):
+    if (train_generator is None or valid_generator is None) and (lo is None or hi is None):
+        raise ValueError(f"Either generator is not provided, {names[0]} and {names[1]} should be both provided: "
+                         f"got {names[0]}={lo}, {names[1]}={hi}, train_generator={train_generator}, "
+                         f"valid_generator={valid_generator}")
+
+
+class Solver1D(BaseSolver):
+    """ODE solver (reference solvers.py:1020-1181): one coordinate ``t``."""
+    N_COORDS = 1
+
+    def __init__(self, ode_system, conditions, t_min=None, t_max=None, nets=None, train_generator=None,
+                 valid_generator=None, analytic_solutions=None, optimizer=None, loss_fn=None, n_batches_train=1,
+                 n_batches_valid=4, metrics=None, n_output_units=1, batch_size=None, shuffle=None, **kw):
+        _need_bounds(t_min, t_max, ("t_min", "t_max"), train_generator, valid_generator)
+        if train_generator is None:
+            train_generator = Generator1D(32, t_min=t_min, t_max=t_max, method="equally-spaced-noisy")
+        if valid_generator is None:
+            valid_generator = Generator1D(32, t_min=t_min, t_max=t_max, method="equally-spaced")
+        self.t_min, self.t_max = t_min, t_max
+        super().__init__(diff_eqs=ode_system, conditions=conditions, nets=nets, train_generator=train_generator,
+                         valid_generator=valid_generator, analytic_solutions=analytic_solutions, optimizer=optimizer,
+                         loss_fn=loss_fn, n_batches_train=n_batches_train, n_batches_valid=n_batches_valid,
+                         metrics=metrics, n_input_units=1, n_output_units=n_output_units, shuffle=shuffle,
+                         batch_size=batch_size, **kw)
+
+    def _solution_class(self):
+        return Solution1D
+
+    def _get_internal_variables(self):
+        d = super()._get_internal_variables()
+        d.update({"t_min": self.t_min, "t_max": self.t_max})
+        return d
+
+
+class Solver2D(BaseSolver):
+    """2-D PDE solver (reference solvers.py:1427-1593): coordinates ``(x, y)``."""
+    N_COORDS = 2
+
+    def __init__(self, pde_system, conditions, xy_min=None, xy_max=None, nets=None, train_generator=None,
+                 valid_generator=None, analytic_solutions=None, optimizer=None, loss_fn=None, n_batches_train=1,
+                 n_batches_valid=4, metrics=None, n_output_units=1, batch_size=None, shuffle=None, **kw):
+        _need_bounds(xy_min, xy_max, ("xy_min", "xy_max"), train_generator, valid_generator)
+        if train_generator is None:
+            train_generator = Generator2D((32, 32), xy_min=xy_min, xy_max=xy_max, method="equally-spaced-noisy")
+        if valid_generator is None:
+            valid_generator = Generator2D((32, 32), xy_min=xy_min, xy_max=xy_max, method="equally-spaced")
+        self.xy_min, self.xy_max = xy_min, xy_max
+        super().__init__(diff_eqs=pde_system, conditions=conditions, nets=nets, train_generator=train_generator,
+                         valid_generator=valid_generator, analytic_solutions=analytic_solutions, optimizer=optimizer,
+                         loss_fn=loss_fn, n_batches_train=n_batches_train, n_batches_valid=n_batches_valid,
+                         metrics=metrics, n_input_units=2, n_output_units=n_output_units, shuffle=shuffle,
+                         batch_size=batch_size, **kw)
+
+    def _solution_class(self):
+        return Solution2D
+
+    def _get_internal_variables(self):
+        d = super()._get_internal_variables()
+        d.update({"xy_min": self.xy_min, "xy_max": self.xy_max})
+        return d
+
+
+class SolverSpherical(BaseSolver):
+    """Spherical PDE solver (reference solvers.py:761-974): coordinates ``(r, theta, phi)``; a condition receives only
+    as many leading coordinates as its ``parameterize`` / ``enforce`` takes (``_auto_enforce``, :894-916)."""
+    N_COORDS = 3
+
+    def __init__(self, pde_system, conditions, r_min=None, r_max=None, nets=None, train_generator=None,
+                 valid_generator=None, analytic_solutions=None, optimizer=None, loss_fn=None, n_batches_train=1,
+                 n_batches_valid=4, metrics=None, enforcer=None, n_output_units=1, shuffle=None, batch_size=None,
+                 **kw):
+        _need_bounds(r_min, r_max, ("r_min", "r_max"), train_generator, valid_generator)
+        if enforcer is not None:
+            raise NotImplementedError("custom `enforcer` callables are not supported by the fused SolverSpherical")
+        if train_generator is None:
+            train_generator = GeneratorSpherical(512, r_min, r_max, method="equally-spaced-noisy")
+        if valid_generator is None:
+            valid_generator = GeneratorSpherical(512, r_min, r_max, method="equally-spaced-noisy")
+        self.r_min, self.r_max, self.enforcer = r_min, r_max, enforcer
+        super().__init__(diff_eqs=pde_system, conditions=conditions, nets=nets, train_generator=train_generator,
+                         valid_generator=valid_generator, analytic_solutions=analytic_solutions, optimizer=optimizer,
+                         loss_fn=loss_fn, n_batches_train=n_batches_train, n_batches_valid=n_batches_valid,
+                         metrics=metrics, n_input_units=3, n_output_units=n_output_units, shuffle=shuffle,
+                         batch_size=batch_size, **kw)
+
+    def _coords_for_condition(self, k, cond, coords):
+        if cond.__class__.enforce == BaseCondition.enforce:
+            n_params = len(signature(cond.parameterize).parameters)
+        else:
+            n_params = len(signature(cond.enforce).parameters)
+        return tuple(coords[:n_params - 1])
+
+    def _solution_class(self):
+        return SolutionSpherical
+
+    def _get_internal_variables(self):
+        d = super()._get_internal_variables()
+        d.update({"r_min": self.r_min, "r_max": self.r_max, "enforcer": self.enforcer})
+        return d
+
+
+class BundleSolver1D(BaseSolver):
+    """Bundle ODE solver (reference solvers.py:1189-1419): coordinates ``(t, theta_1..theta_k)``; the ODE receives
+    ``(*funcs, t, *theta[eq_param_index])`` (``_diff_eqs_wrapper``, :1353-1361)."""
+
+    def __init__(self, ode_system, conditions, t_min=None, t_max=None, theta_min=None, theta_max=None,
+                 eq_param_index=(), nets=None, train_generator=None, valid_generator=None, analytic_solutions=None,
+                 optimizer=None, loss_fn=None, n_batches_train=1, n_batches_valid=4, metrics=None, n_output_units=1,
+                 batch_size=None, shuffle=None, **kw):
+        _need_bounds(t_min, t_max, ("t_min", "t_max"), train_generator, valid_generator)
+        theta_min = (theta_min,) if isinstance(theta_min, (float, int)) else tuple(theta_min or ())
+        theta_max = (theta_max,) if isinstance(theta_max, (float, int)) else tuple(theta_max or ())
+        if len(theta_min) != len(theta_max):
+            raise ValueError(f"length of theta_min and theta_max must be equal, got {len(theta_min)} != {len(theta_max)}")
+        if train_generator is None or valid_generator is None:
+            r_min, r_max = (t_min,) + theta_min, (t_max,) + theta_max
+            n_input_units = len(r_min)
+            if train_generator is None:
+                train_generator = Generator1D(32, t_min=t_min, t_max=t_max, method="equally-spaced-noisy")
+                for i in range(1, n_input_units):
+                    train_generator ^= Generator1D(32, t_min=r_min[i], t_max=r_max[i], method="equally-spaced-noisy")
+            if valid_generator is None:
+                valid_generator = Generator1D(32, t_min=t_min, t_max=t_max, method="equally-spaced")
+                for i in range(1, n_input_units):
+                    valid_generator ^= Generator1D(32, t_min=r_min[i], t_max=r_max[i], method="equally-spaced")
+            self.r_min, self.r_max = r_min, r_max
+        else:
+            self.r_min, self.r_max = (t_min,) + theta_min, (t_max,) + theta_max
+            n_input_units = len(SamplerGenerator(train_generator).get_examples())
+        self._n_funcs_1 = len(conditions) + 1
+        self._ode_system = ode_system
+        self.eq_param_index = tuple(self._n_funcs_1 + idx for idx in eq_param_index)
+        super().__init__(diff_eqs=ode_system, conditions=conditions, nets=nets, train_generator=train_generator,
+                         valid_generator=valid_generator, analytic_solutions=analytic_solutions, optimizer=optimizer,
+                         loss_fn=loss_fn, n_batches_train=n_batches_train, n_batches_valid=n_batches_valid,
+                         metrics=metrics, n_input_units=n_input_units, n_output_units=n_output_units, shuffle=shuffle,
+                         batch_size=batch_size, **kw)
+
+    def _traced_diff_eqs(self, *variables):
+        head = variables[:self._n_funcs_1]
+        return self._ode_system(*head, *(variables[i] for i in self.eq_param_index))
+
+    def _solution_class(self):
+        return BundleSolution1D
+
+    def _get_internal_variables(self):
+        d = super()._get_internal_variables()
+        d.update({"r_min": self.r_min, "r_max": self.r_max, "eq_param_index": self.eq_param_index})
+        return d

@@ -86,7 +86,7 @@ class TracedProblem:
         for k, (net, cond) in enumerate(zip(nets, conditions)):
             cc = coords if coords_for_condition is None else coords_for_condition(k, cond, coords)
             funcs.append(g.lift(cond.enforce(net, *cc)))
-        res = diff_eqs(*funcs, *coords)
+        res = diff_eqs(*funcs, *coords) if diff_eqs is not None else []   # None: solution-only problem (u, no residual)
         if isinstance(res, S.Sym) or not hasattr(res, "__len__"):
             res = [res]
         residuals = [g.lift(r) for r in res]

@@ -1,0 +1,72 @@
+"""N>1 host logic on CPU: two gloo ranks shard a batch, compute partial gradients with the GLOBAL loss scale (numpy
+mirror of the kernels = test infrastructure), all-reduce the flat [grad | sum r^2] buffer and must reproduce the
+single-process result of the reference (golden vectors)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, key, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import workloads
+    from conftest import load_golden
+    from helpers import product_namespace
+    from neurodiffeq_b200.tracing import TracedProblem
+    from neurodiffeq_b200.parallel import shard_bounds, all_reduce_gradbuf
+    from oracle import jet_numpy
+    wl = workloads.build(product_namespace(), key)
+    gold = load_golden(wl.name)
+    nets, conds = wl.make_nets(), wl.make_conditions()
+    tp = TracedProblem(nets, conds, workloads.bundle_eq_wrapper(wl), len(wl.coord_names))
+    per_net, it = [], iter(gold["params"])
+    for nd in tp.nets:
+        per_net.append([next(it) for _ in range(2 * len(nd.linears))])
+    n = gold["coords"].shape[1]
+    lo, hi = shard_bounds(n, rank, world)
+    out = jet_numpy.run_traced(tp, per_net, gold["coords"][:, lo:hi], n_global=n)
+    flat = np.concatenate([g.reshape(-1) for g in out["grads"]] + [np.array([(out["residual"] ** 2).sum()])])
+    buf = torch.from_numpy(flat)
+    all_reduce_gradbuf(buf, dist)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "buf.npy"), buf.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("key", ["c2", "c5"])
+def test_two_rank_sharding_reproduces_single_process_gradient(key, tmp_path):
+    from conftest import load_golden
+    import workloads
+    from helpers import product_namespace
+    world = 2
+    port = 29000 + (os.getpid() % 2000)
+    mp.start_processes(_worker, args=(world, port, key, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    buf = np.load(os.path.join(str(tmp_path), "buf.npy"))
+    wl = workloads.build(product_namespace(), key)
+    gold = load_golden(wl.name)
+    flat = np.concatenate([g.reshape(-1) for g in gold["grads"]])
+    n = gold["coords"].shape[1]
+    assert np.linalg.norm(buf[:-1] - flat) <= 1e-9 * np.linalg.norm(flat)
+    assert abs(buf[-1] / (n * gold["residual"].shape[0]) - gold["loss"]) <= 1e-10 * gold["loss"]
+
+
+def test_shard_bounds_tile_the_batch():
+    from neurodiffeq_b200.parallel import shard_bounds
+    for n in (1, 7, 16384, 65537):
+        for w in (1, 2, 3, 8):
+            edges = [shard_bounds(n, r, w) for r in range(w)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(edges[:-1], edges[1:]))
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1

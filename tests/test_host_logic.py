@@ -1,0 +1,123 @@
+"""CPU tests of the host-side mirror: generators, solver construction errors, program lowering details."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from neurodiffeq_b200 import generators as G
+from neurodiffeq_b200 import symbolic as S
+
+
+def test_generator1d_methods_shapes_and_bounds():
+    for method in ("uniform", "equally-spaced", "equally-spaced-noisy", "log-spaced", "log-spaced-noisy", "chebyshev",
+                   "chebyshev1", "chebyshev2", "chebyshev2-noisy", "latin-hypercube"):
+        g = G.Generator1D(64, t_min=0.1, t_max=2.0, method=method)
+        x = g.get_examples()
+        assert x.shape == (64,) and x.dtype == torch.float32 and not x.requires_grad
+        if "noisy" not in method:
+            assert x.min() >= 0.1 - 1e-6 and x.max() <= 2.0 + 1e-6
+    with pytest.raises(ValueError):
+        G.Generator1D(8, method="nope")
+    with pytest.raises(ValueError):
+        G.Generator1D(8, t_min=-1.0, t_max=1.0, method="log-spaced")
+    g = G.Generator1D(1024, 0.1, 12.0, "equally-spaced-noisy")
+    assert abs(g.noise_std - (11.9 / 1024) / 4) < 1e-12           # reference generators.py:149
+    base = torch.linspace(0.1, 12.0, 1024)
+    assert (g.get_examples() - base).abs().max() < 8 * g.noise_std
+
+
+def test_generator2d_and_3d():
+    g = G.Generator2D((16, 8), (0, -1), (1, 1), "equally-spaced")
+    x, y = g.get_examples()
+    assert g.size == 128 and x.shape == (128,) and y.shape == (128,)
+    assert torch.allclose(x[:8], torch.zeros(8)) and torch.allclose(y[:8], torch.linspace(-1, 1, 8))   # 'ij' order
+    gn = G.Generator2D((128, 128), (0, 0), (1, 1), "equally-spaced-noisy")
+    xn, yn = gn.get_examples()
+    xg, yg = G.Generator2D((128, 128), (0, 0), (1, 1), "equally-spaced").get_examples()
+    assert (xn - xg).std() == pytest.approx(1 / 128 / 4, rel=0.1)   # N(0, (step/4)^2), generators.py:253-266
+    g3 = G.Generator3D((4, 5, 6))
+    assert g3.size == 120 and len(g3.get_examples()) == 3
+    with pytest.raises(ValueError):
+        G.Generator2D(method="bad")
+
+
+def test_generator_spherical():
+    g = G.GeneratorSpherical(4096, 0.1, 3.0)
+    r, th, ph = g.get_examples()
+    assert r.min() >= 0.1 and r.max() <= 3.0
+    assert th.min() > 0 and th.max() < math.pi and ph.min() >= 0 and ph.max() <= 2 * math.pi + 1e-5
+    assert torch.sin(th).min() > 1e-4              # never exactly on a pole
+    assert abs((r ** 2).mean().item() - (0.01 + 9.0) / 2) < 0.2   # r^2 uniform
+    with pytest.raises(ValueError):
+        G.GeneratorSpherical(8, 2.0, 1.0)
+
+
+def test_combinators():
+    a, b = G.Generator1D(8, method="equally-spaced"), G.Generator1D(8, 2, 3, method="equally-spaced")
+    assert (a + b).get_examples().shape == (16,) and (a + b).size == 16
+    e = (a * b).get_examples()
+    assert len(e) == 2 and e[0].shape == (8,) and (a * b).size == 8
+    m = (a ^ b ^ G.Generator1D(4)).get_examples()
+    assert len(m) == 3 and m[0].shape == (256,) and (a ^ b ^ G.Generator1D(4)).size == 256
+    with pytest.raises(ValueError):
+        G.EnsembleGenerator(a, G.Generator1D(9))
+    st = G.StaticGenerator(G.Generator1D(8))
+    assert torch.equal(st.get_examples(), st.get_examples())
+    pre = G.PredefinedGenerator(np.arange(4.0), np.ones(4))
+    assert [t.shape for t in G.SamplerGenerator(pre).get_examples()] == [(4, 1), (4, 1)]
+    with pytest.raises(ValueError):
+        a + 3
+
+
+def test_register_allocation_is_small_and_interpreter_matches():
+    """liveness-based slot reuse keeps the value file tiny; the numpy interpreter reproduces a closed form."""
+    g = S.Graph()
+    x, y = g.coord(0), g.coord(1)
+    n = g.ych(0, 0, 0)
+    expr = (x * y + torch.sin(3.0 * x)) / (1.0 + y * y) + n * torch.exp(-x)
+    prog = S.lower([(S.OP_ST_U, 0, expr), (S.OP_ST_R, 0, expr * expr - 2.0)], lambda a, b, c: 0)
+    assert prog.n_slots <= 6
+    rs = np.random.RandomState(0)
+    c = rs.rand(2, 50)
+    yv = rs.rand(1, 50)
+    u, r, _ = S.evaluate_program(prog, c, yv, n_u=1, n_r=1)
+    want = (c[0] * c[1] + np.sin(3 * c[0])) / (1 + c[1] ** 2) + yv[0] * np.exp(-c[0])
+    np.testing.assert_allclose(u[0], want, rtol=1e-12)
+    np.testing.assert_allclose(r[0], want ** 2 - 2, rtol=1e-12)
+
+
+def test_symbolic_reverse_matches_finite_differences():
+    g = S.Graph()
+    x = g.coord(0)
+    n0, n1 = g.ych(0, 0, 0), g.ych(0, 0, 1)
+    r = torch.tanh(n0 * x) + n1 ** 2 / (1.0 + x) - torch.cos(n0)
+    adj = S.reverse_gradients([(r, g.const(1.0))])
+    rows = {n0: 0, n1: 1}
+    prog = S.lower([(S.OP_ST_R, 0, r)] + [(S.OP_ST_SEED, rows[k], v) for k, v in adj.items()],
+                   lambda a, b, c: c)
+    rs = np.random.RandomState(1)
+    c, yv = rs.rand(1, 20) + 0.5, rs.rand(2, 20)
+    _, r0, seed = S.evaluate_program(prog, c, yv, n_r=1, n_seed=2)
+    for k in range(2):
+        h = 1e-6
+        yp, ym = yv.copy(), yv.copy()
+        yp[k] += h
+        ym[k] -= h
+        fd = (S.evaluate_program(prog, c, yp, n_r=1, n_seed=2)[1] - S.evaluate_program(prog, c, ym, n_r=1, n_seed=2)[1]) / (2 * h)
+        np.testing.assert_allclose(seed[k], fd[0], rtol=1e-6, atol=1e-8)
+
+
+def test_unsupported_features_raise_loudly():
+    from neurodiffeq_b200.tracing import TracedProblem
+    from neurodiffeq_b200.networks import FCNN
+    from neurodiffeq_b200.conditions import NoCondition, IBVP1D
+    from neurodiffeq_b200 import diff
+    import torch.nn as nn
+    with pytest.raises(NotImplementedError):   # activation without a jet rule
+        TracedProblem([FCNN(1, 1, actv=nn.ReLU)], [NoCondition()], lambda u, t: [diff(u, t)], 1)
+    with pytest.raises(NotImplementedError):   # Neumann IBVP evaluates the net at boundary points
+        IBVP1D(0, 1, 0, lambda x: x, x_min_prime=lambda t: 0, x_max_val=lambda t: 0).enforce(
+            FCNN(2, 1), S.Graph().coord(0), S.Graph().coord(1))
+    with pytest.raises(NotImplementedError):   # torch.cat of traced columns outside enforce()
+        TracedProblem([FCNN(1, 1)], [NoCondition()], lambda u, t: [torch.cat([u, t], 1)], 1)
