@@ -61,7 +61,7 @@ constexpr int PROG_MAX = 1024;
 
 // Weight-ring depth: keep all chunks resident if that still allows `target_occ` CTAs per SM; otherwise stream with as many
 // stages as fit (>= 2), giving up one CTA per SM at a time.  Returns -1 if nothing fits.
-static int pick_stages(int fixed_bytes, int chunks, int target_occ) {
+static int pick_stages(int fixed_bytes, int chunks, int target_occ, bool resident_only = false) {
     if (chunks == 0) return fixed_bytes <= SMEM_LIMIT ? 1 : -1;
     const int per_sm = 233472 - 1024;   // 228 KB per SM minus reserve
     for (int occ = target_occ; occ >= 1; --occ) {
@@ -70,7 +70,7 @@ static int pick_stages(int fixed_bytes, int chunks, int target_occ) {
         int ns = (budget - fixed_bytes) / (CHUNK_FLOATS * 4);
         if (ns > MAX_STAGES) ns = MAX_STAGES;
         if (ns > chunks) ns = chunks;
-        if (ns >= 2 || (ns >= 1 && ns >= chunks)) return ns;
+        if (ns >= chunks || (ns >= 2 && !resident_only)) return ns;
     }
     return -1;
 }
@@ -120,6 +120,20 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int ntc_re
     if ((pl.T / pl.P) % 8 != 0 || pl.T > pl.ntc) return fail(-3, "internal: tile %d unsupported", pl.T);
     pl.RS = C * pl.T + ROW_PAD;
     pl.n_tiles = (int)((N + pl.T - 1) / pl.T);
+    // K1: 8 units per thread (half the shared-memory wavefronts per FFMA2 of the 4-unit tile); its tile is a multiple of T
+    pl.ntc1 = hmax <= 64 ? 128 : 256;
+    pl.P1 = C <= 2 ? 4 : 2;
+    pl.Q1 = hmax > 64 ? 8 : 4;   // wide nets are GEMM-bound (fewer smem wavefronts); narrow ones want more CTAs per SM
+    pl.T1 = pl.ntc1 * pl.P1 * pl.Q1 / hmax;
+    if (pl.T1 < pl.T) {   // K2 fell back to one 256-thread CTA per SM: give K1 the same tile
+        pl.ntc1 = 256;
+        pl.T1 = pl.ntc1 * pl.P1 * pl.Q1 / hmax;
+    }
+    if ((pl.T1 / pl.P1) % 8 != 0 || pl.T1 % pl.T != 0)
+        return fail(-3, "internal: forward tile %d unsupported (backward tile %d)", pl.T1, pl.T);
+    pl.RS1 = C * pl.T1 + ROW_PAD;
+    pl.epi_batch = pl.T1 > 32 ? pl.T1 : 32;   // whole tiles; the program warp walks it 32 points at a time
+    pl.n_tiles1 = (int)((N + pl.T1 - 1) / pl.T1);
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return fail(-4, "cannot query the CUDA device");
@@ -170,18 +184,21 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int ntc_re
     const int small_bytes = round_up(pl.small_floats * 4, 128);
     const int misc_bytes = 256;
     {   // K1: act | ring | small | ycache | slots | misc | prog
-        const int fixed = jet_bytes + small_bytes + sp.n_yrows * pl.ntc * 4 + sp.n_slots * pl.ntc * 4 + misc_bytes +
+        const int act_bytes = hmax * pl.RS1 * 4;
+        const int ycache_bytes = 2 * sp.n_yrows * pl.epi_batch * 4, slots_bytes = sp.n_slots * 32 * 4;
+        const int fixed = act_bytes + small_bytes + ycache_bytes + slots_bytes + misc_bytes +
                           prog_len * 16;
-        const int ns = pick_stages(fixed, pl.chunks_fwd, pl.ntc == 128 ? 3 : 1);
+        // 128-thread forward CTAs share one service warp between weight loading and the residual program -> resident only
+        const int ns = pick_stages(fixed, pl.chunks_fwd, pl.ntc1 == 128 ? 3 : 1, pl.ntc1 == 128);
         if (ns < 0) return fail(-2, "forward kernel does not fit in shared memory");
-        pl.n_stage = ns;   // forward value; the backward value is stored in resident_bwd's companion below
+        pl.n_stage = ns;
         pl.resident_fwd = ns >= pl.chunks_fwd;
         int o = 0;
-        pl.k1_act = o; o += jet_bytes;
+        pl.k1_act = o; o += act_bytes;
         pl.k1_ring = o; o += ns * CHUNK_FLOATS * 4;
         pl.k1_small = o; o += small_bytes;
-        pl.k1_ycache = o; o += sp.n_yrows * pl.ntc * 4;
-        pl.k1_slots = o; o += sp.n_slots * pl.ntc * 4;
+        pl.k1_ycache = o; o += ycache_bytes;
+        pl.k1_slots = o; o += slots_bytes;
         pl.k1_misc = o; o += misc_bytes;
         pl.k1_prog = o; o += prog_len * 16;
         pl.k1_bytes = o;
@@ -209,13 +226,13 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int ntc_re
     // ---- persistent grids: resident CTAs per SM x SMs, capped by the number of tiles ----
     {
         const SchemeEntry* e = find_scheme(sp.n1, sp.n2);
-        const int o1 = e->occ(1, pl.ntc, pl.k1_bytes), o2 = e->occ(2, pl.ntc, pl.k2_bytes);
+        const int o1 = e->occ((pl.ntc1 == 256 && pl.Q1 == 4) ? 3 : 1, pl.ntc1, pl.k1_bytes), o2 = e->occ(2, pl.ntc, pl.k2_bytes);
         if (o1 < 1 || o2 < 1) return fail(-2, "kernel does not fit on an SM (occupancy %d / %d, smem %d / %d B)", o1, o2,
                                           pl.k1_bytes, pl.k2_bytes);
-        pl.grid = pl.n_tiles < sms * o1 ? pl.n_tiles : sms * o1;
+        pl.grid = pl.n_tiles1 < sms * o1 ? pl.n_tiles1 : sms * o1;
         pl.grid_bwd = pl.n_tiles < sms * o2 ? pl.n_tiles : sms * o2;
         if (pl.grid > 640) pl.grid = 640;   // loss partials live in the first 2.5 KB of the workspace
-        *occ_min = o1 < o2 ? o1 : o2;
+        *occ_min = o2;
     }
     // ---- workspace ----
     long long zt = 0;

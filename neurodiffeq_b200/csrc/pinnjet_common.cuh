@@ -34,7 +34,10 @@ enum : int {
 
 // Everything derived from (spec, N): identical on host and device, computed by make_plan() in pinnjet_api.cu.
 struct Plan {
-    int T, P, Q, C, RS;                  // tile points, thread tile, channels, jet row stride (floats)
+    int T, P, Q, C, RS;                  // K2 tile: points, thread tile, channels, jet row stride (floats); also the
+                                         // layout of the z-jet records and seeds K1 leaves in the workspace
+    int epi_batch;                       // points per residual-program batch (jet table double-buffered in smem)
+    int T1, P1, Q1, RS1, ntc1, n_tiles1; // K1 tile (a multiple of T): wider thread tile (Q1 = 8) -> fewer smem wavefronts
     int n_tiles, grid, grid_bwd, hmax, ntc;   // grid: K1 CTAs (= loss partials), grid_bwd: K2 CTAs (= gradient partials)
     int n_stage, n_stage_bwd, resident_fwd, resident_bwd, chunks_fwd, chunks_bwd;   // n_stage: forward ring
     int hp[PJ_MAX_NETS][PJ_MAX_LINEAR + 1];   // padded widths (hidden -> multiple of 32; input/output unpadded)
@@ -170,9 +173,27 @@ __device__ __forceinline__ float pg_sum(float v) {
 // ---------------------------------------------------------------------------------------------------------------------
 // activation jets.  Channels: 0 value | 1..N1 first order | N1+1..N1+N2 pure second order.
 // ---------------------------------------------------------------------------------------------------------------------
+// Branch-free tanh, ~1-4 ulp: |x| < 0.6: x + x^3 P(x^2) (degree-4 minimax fit, 1.4 ulp); else 1 - 2/(exp(2|x|)+1) with
+// ex2.approx / rcp.approx.  Straight-line code: the 8-16 independent calls of an activation epilogue pipeline instead of
+// diverging like libdevice's tanhf.
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float ax = fabsf(x), t = x * x;
+    float p = fmaf(-0.006276387721300125f, t, 0.021116213873028755f);
+    p = fmaf(p, t, -0.053875137120485306f);
+    p = fmaf(p, t, 0.13332924246788025f);
+    p = fmaf(p, t, -0.3333333134651184f);
+    const float small = fmaf(x * t, p, x);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(ax, 15.0f) * 2.885390081777927f));
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    const float big = copysignf(fmaf(-2.0f, r, 1.0f), x);
+    return ax < 0.6f ? small : big;
+}
+
 __device__ __forceinline__ void act_d2(int act, float z0, float& a0, float& s1, float& s2) {
     if (act == PJ_ACT_TANH) {
-        a0 = tanhf(z0);
+        a0 = tanh_fast(z0);
         s1 = fmaf(-a0, a0, 1.0f);
         s2 = -2.0f * a0 * s1;
     } else {

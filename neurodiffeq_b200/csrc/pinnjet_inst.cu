@@ -56,6 +56,7 @@ cudaError_t launch_loss_finalize(const float* part, int n_parts, float* out, cud
 constexpr int kC = 1 + PJ_N1 + PJ_N2;
 constexpr int kP = (kC <= 2) ? 4 : 2;   // must match make_plan() in pinnjet_api.cu
 constexpr int kQ = 4;
+constexpr int kP1 = kP, kQ1 = 8;        // K1 thread tile (make_plan: P1, Q1)
 // CTAs per SM the register allocation is tuned for (shared memory may allow fewer): 128-thread CTAs share an SM
 constexpr int kMinB1_128 = 3, kMinB2_128 = 2;
 
@@ -69,14 +70,19 @@ static cudaError_t configure(K kern, int& configured) {
 
 cudaError_t PJ_NAME(launch_k1_, PJ_N1, PJ_N2)(const K1Args& a, int grid, int smem, cudaStream_t s) {
     static int c128 = 0, c256 = 0;
-    if (a.plan.ntc == 128) {
-        auto kern = k1_forward_kernel<128, kMinB1_128, kP, kQ, PJ_N1, PJ_N2>;
+    if (a.plan.ntc1 == 128) {
+        auto kern = k1_forward_kernel<128, kMinB1_128, kP1, 4, PJ_N1, PJ_N2>;
         if (cudaError_t e = configure(kern, c128)) return e;
         kern<<<grid, 160, smem, s>>>(a);
-    } else {
-        auto kern = k1_forward_kernel<256, 1, kP, kQ, PJ_N1, PJ_N2>;
+    } else if (a.plan.Q1 == 8) {
+        auto kern = k1_forward_kernel<256, 1, kP1, kQ1, PJ_N1, PJ_N2>;
         if (cudaError_t e = configure(kern, c256)) return e;
-        kern<<<grid, 288, smem, s>>>(a);
+        kern<<<grid, 320, smem, s>>>(a);
+    } else {
+        static int c256q4 = 0;
+        auto kern = k1_forward_kernel<256, 1, kP1, 4, PJ_N1, PJ_N2>;
+        if (cudaError_t e = configure(kern, c256q4)) return e;
+        kern<<<grid, 320, smem, s>>>(a);
     }
     return cudaGetLastError();
 }
@@ -101,13 +107,20 @@ int PJ_NAME(occupancy_, PJ_N1, PJ_N2)(int which, int ntc, int smem) {
     cudaError_t e;
     static int c[4] = {0, 0, 0, 0};
     if (which == 1 && ntc == 128) {
-        auto kern = k1_forward_kernel<128, kMinB1_128, kP, kQ, PJ_N1, PJ_N2>;
+        auto kern = k1_forward_kernel<128, kMinB1_128, kP1, 4, PJ_N1, PJ_N2>;
         configure(kern, c[0]);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 160, smem);
-    } else if (which == 1) {
-        auto kern = k1_forward_kernel<256, 1, kP, kQ, PJ_N1, PJ_N2>;
-        configure(kern, c[1]);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 288, smem);
+    } else if (which == 1 || which == 3) {   // 3: 256-thread K1 with the 4-unit tile (narrow nets without room for 2 CTAs)
+        if (which == 1) {
+            auto kern = k1_forward_kernel<256, 1, kP1, kQ1, PJ_N1, PJ_N2>;
+            configure(kern, c[1]);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 320, smem);
+        } else {
+            static int cq4 = 0;
+            auto kern = k1_forward_kernel<256, 1, kP1, 4, PJ_N1, PJ_N2>;
+            configure(kern, cq4);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 320, smem);
+        }
     } else if (ntc == 128) {
         auto kern = k2_backward_kernel<128, kMinB2_128, kP, kQ, PJ_N1, PJ_N2>;
         configure(kern, c[2]);

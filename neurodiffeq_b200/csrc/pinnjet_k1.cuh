@@ -68,10 +68,48 @@ struct RingCursor {
     }
 };
 
-template <int NTC, int MINB, int P, int Q, int N1, int N2>
-__global__ void __launch_bounds__(NTC + 32, MINB) k1_forward_kernel(const __grid_constant__ K1Args A) {
+// z-jets of P points of one unit (registers) -> workspace record (train), activation-jet rule, a-jets -> shared memory.
+// Record channel 0 holds tanh(z0) for tanh nets (the reverse pass then needs no transcendental) and z0 for sin nets.
+template <int P, int N1, int N2>
+__device__ __forceinline__ void finish_unit(float (&zq)[P][1 + N1 + N2], int act_kind, float* __restrict__ act_row, int T,
+                                            float* __restrict__ rec_row, int T2) {
     constexpr int C = 1 + N1 + N2;
-    constexpr int NT_COMPUTE = NTC, NT_TOTAL = NTC + 32, N_CWARPS = NTC / 32, EPI_BATCH = NTC;
+    auto store = [](float* dst, const float (&v)[P][C], int c) {
+        if constexpr (P == 4)
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0][c], v[1][c], v[2][c], v[3][c]);
+        else
+            *reinterpret_cast<float2*>(dst) = make_float2(v[0][c], v[1][c]);
+    };
+    float z0s[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) z0s[p] = zq[p][0];
+    if (rec_row) {
+#pragma unroll
+        for (int c = 1; c < C; ++c) store(rec_row + c * T2, zq, c);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) act_forward<N1, N2>(act_kind, zq[p]);
+    if (rec_row) {
+        if (act_kind == PJ_ACT_TANH) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) z0s[p] = zq[p][0];
+        }
+        if constexpr (P == 4)
+            *reinterpret_cast<float4*>(rec_row) = make_float4(z0s[0], z0s[1], z0s[2], z0s[3]);
+        else
+            *reinterpret_cast<float2*>(rec_row) = make_float2(z0s[0], z0s[1]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) store(act_row + c * T, zq, c);
+}
+
+template <int NTC, int MINB, int P, int Q, int N1, int N2>
+__global__ void __launch_bounds__(NTC + (NTC == 128 ? 32 : 64), MINB) k1_forward_kernel(const __grid_constant__ K1Args A) {
+    constexpr int C = 1 + N1 + N2;
+    // service warps after the compute warps: 128-thread CTAs (weights always resident: the producer only issues the initial
+    // loads) use ONE warp as producer-then-program warp; 256-thread CTAs have a producer warp and a program warp
+    constexpr int N_SVC = NTC == 128 ? 1 : 2;
+    constexpr int NT_COMPUTE = NTC, NT_TOTAL = NTC + 32 * N_SVC, N_CWARPS = NTC / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     const PjSpec& sp = A.spec;
     const Plan& pl = A.plan;
@@ -83,26 +121,66 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k1_forward_kernel(const __grid
     int4* prog_s = reinterpret_cast<int4*>(smem + pl.k1_prog);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + pl.k1_misc);
     uint64_t* empty = full + MAX_STAGES;
-    float* red = reinterpret_cast<float*>(empty + MAX_STAGES);   // [N_CWARPS] per-warp sum of r^2
+    uint64_t* yfull = empty + MAX_STAGES;    // [2] jet table of a batch complete -> program warp
+    uint64_t* yempty = yfull + 2;            // [2] program warp done with the buffer
+    const int EB = pl.epi_batch;             // batch capacity in points (a whole number of tiles)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int T = pl.T, RS = pl.RS;
-    const int my_tiles = (pl.n_tiles > (int)blockIdx.x) ? (pl.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int T = pl.T1, RS = pl.RS1;      // this kernel's tile
+    const int T2 = pl.T, RS2 = pl.RS;      // K2's tile = layout of the workspace records
+    const long long ws_points = (long long)pl.n_tiles * T2;   // points the workspace has room for
+    const int my_tiles = (pl.n_tiles1 > (int)blockIdx.x) ? (pl.n_tiles1 - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (tid == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], N_CWARPS);
         }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&yfull[b], 1);
+            mbar_init(&yempty[b], 1);
+        }
         fence_barrier_init();
     }
     for (int i = tid; i < pl.small_floats; i += NT_TOTAL) small[i] = __ldg(A.pack + i);
     for (int i = tid; i < A.prog_len; i += NT_TOTAL) prog_s[i] = __ldg(A.prog + i);
-    if (tid < N_CWARPS) red[tid] = 0.0f;
     __syncthreads();
 
     if (warp == N_CWARPS) {   // ---------------- producer warp ----------------
         if (lane == 0) weight_producer<true>(sp, pl, A.pack, ring, full, empty, my_tiles);
+        if constexpr (N_SVC == 2) return;
+        __syncwarp();
+    }
+    const int tiles_per_batch = EB / T;
+    if (warp == N_CWARPS + N_SVC - 1) {   // ---------------- program warp: residual program of batch b while the compute warps
+        //                                             already work on the tiles of batch b+1 ----------------
+        const bool train_pw = A.mode == 1;
+        float my_sumsq = 0.0f;
+        const int n_batches = (my_tiles + tiles_per_batch - 1) / tiles_per_batch;
+        for (int b = 0; b < n_batches; ++b) {
+            const int buf = b & 1;
+            mbar_wait(&yfull[buf], (uint32_t)((b >> 1) & 1));
+            const float* yb = ycache + (size_t)buf * sp.n_yrows * EB;
+            const int first_iter = b * tiles_per_batch;
+            const int npts = min(tiles_per_batch, my_tiles - first_iter) * T;
+            for (int bp = lane; bp < npts; bp += 32) {
+                const int tl = bp / T, pt = bp - tl * T;
+                const long long btile = (long long)blockIdx.x + (long long)(first_iter + tl) * gridDim.x;
+                const long long gidx = btile * T + pt;
+                float* seed_tile = (train_pw && gidx < ws_points)
+                                       ? A.seeds + (gidx / T2) * ((long long)sp.n_yrows * T2) + (gidx % T2) : nullptr;
+                if (gidx < A.N) {
+                    ProgIO io{A.coords, gidx, A.N, yb + bp, EB, A.rbar, A.loss_scale, A.u_out, A.r_out, seed_tile, T2};
+                    my_sumsq += run_program<32>(prog_s, A.prog_len, slots + lane, io);
+                } else if (seed_tile) {
+                    for (int r = 0; r < sp.n_yrows; ++r) seed_tile[r * T2] = 0.0f;   // padded points: zero adjoint
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&yempty[buf]);
+        }
+        my_sumsq = warp_sum(my_sumsq);
+        if (lane == 0) A.loss_part[blockIdx.x] = my_sumsq;
         return;
     }
 
@@ -111,8 +189,7 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k1_forward_kernel(const __grid
     const int p0 = jm.p0, u0 = jm.u0;
     RingCursor cur{0, pl.n_stage, pl.resident_fwd != 0, full, empty, ring};
     const bool train = A.mode == 1;
-    float my_sumsq = 0.0f;
-    int batch_n = 0, batch_first_iter = 0;
+    int bslot = 0, batch_idx = 0;   // tile slot inside the current batch, batches handed to the program warp so far
     PJ_T_DECL   // slots: 0 setup, 1 layer0, 2 gemm, 3 barrier-after-gemm, 4 epilogue, 5 output layer, 6 program
     PJ_T_MARK(0)
 
@@ -120,7 +197,16 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k1_forward_kernel(const __grid
         const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
         const long long base = tile * T;
         if (cur.resident) cur.it = 0;
-        float* zj_tile = train ? A.zj + tile * pl.zj_tile_floats : nullptr;
+        if (bslot == 0 && batch_idx >= 2) mbar_wait(&yempty[batch_idx & 1], (uint32_t)(((batch_idx >> 1) - 1) & 1));
+        float* yb = ycache + (size_t)(batch_idx & 1) * sp.n_yrows * EB + bslot * T;
+        // z-jet record of this thread's P points: K2-tile index and column inside it
+        if (iter + 1 < my_tiles) {   // pull the next tile's coordinates towards L1 while this tile computes
+            const long long nb = (tile + gridDim.x) * T + p0;
+            if (nb < A.N)
+                for (int i = 0; i < sp.n_coords; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.coords[i] + nb));
+        }
+        const bool rec = train && (base + p0 < ws_points);
+        float* zj_tile = rec ? A.zj + ((base + p0) / T2) * pl.zj_tile_floats + (p0 % T2) : nullptr;
 
         for (int n = 0; n < sp.n_nets; ++n) {
             const PjNet& net = sp.net[n];
@@ -144,7 +230,7 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k1_forward_kernel(const __grid
                                 x[i][p] = __ldg(A.coords[net.in_coord[i]] + g);
                             }
                         }
-                    float* zrow = train ? zj_tile + pl.zj_off[n][1] : nullptr;
+                    float* zrow = rec ? zj_tile + pl.zj_off[n][1] : nullptr;
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
                         const int u = u0 + q;
@@ -167,28 +253,7 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k1_forward_kernel(const __grid
 #pragma unroll
                             for (int s2 = 0; s2 < N2; ++s2) zq[p][1 + N1 + s2] = 0.0f;
                         }
-                        // workspace record for K2: channels >= 1 are z-jets; channel 0 is tanh(z0) for tanh nets (so that
-                        // the reverse pass needs no transcendental) and z0 for sin nets
-                        float z0s[P];
-#pragma unroll
-                        for (int p = 0; p < P; ++p) z0s[p] = zq[p][0];
-                        if (train) {
-#pragma unroll
-                            for (int c = 1; c < C; ++c)
-#pragma unroll
-                                for (int p = 0; p < P; ++p) zrow[u * RS + c * T + p0 + p] = zq[p][c];
-                        }
-#pragma unroll
-                        for (int p = 0; p < P; ++p) act_forward<N1, N2>(act_kind, zq[p]);
-                        if (train) {
-#pragma unroll
-                            for (int p = 0; p < P; ++p)
-                                zrow[u * RS + p0 + p] = (act_kind == PJ_ACT_TANH) ? zq[p][0] : z0s[p];
-                        }
-#pragma unroll
-                        for (int c = 0; c < C; ++c)
-#pragma unroll
-                            for (int p = 0; p < P; ++p) act[u * RS + c * T + p0 + p] = zq[p][c];
+                        finish_unit<P, N1, N2>(zq, act_kind, act + u * RS + p0, T, rec ? zrow + u * RS2 : nullptr, T2);
                     }
                 }
             }
@@ -217,7 +282,7 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k1_forward_kernel(const __grid
                 PJ_T_MARK(3)
                 if (valid) {
                     const float* bl = small + pl.s_b[n][l];
-                    float* zrow = train ? zj_tile + pl.zj_off[n][l + 1] : nullptr;
+                    float* zrow = rec ? zj_tile + pl.zj_off[n][l + 1] : nullptr;
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
                         const int u = u0 + q;
@@ -227,40 +292,7 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k1_forward_kernel(const __grid
                         for (int c = 0; c < C; ++c)
 #pragma unroll
                             for (int p = 0; p < P; ++p) zq[p][c] = pick<P>(acc[q][c], p) + (c == 0 ? bias : 0.0f);
-                        float z0s[P];
-#pragma unroll
-                        for (int p = 0; p < P; ++p) z0s[p] = zq[p][0];
-                        if (train) {
-#pragma unroll
-                            for (int c = 1; c < C; ++c) {
-                                if constexpr (P == 4)
-                                    *reinterpret_cast<float4*>(zrow + u * RS + c * T + p0) =
-                                        make_float4(zq[0][c], zq[1][c], zq[2][c], zq[3][c]);
-                                else
-                                    *reinterpret_cast<float2*>(zrow + u * RS + c * T + p0) =
-                                        make_float2(zq[0][c], zq[1][c]);
-                            }
-                        }
-#pragma unroll
-                        for (int p = 0; p < P; ++p) act_forward<N1, N2>(act_kind, zq[p]);
-                        if (train) {
-                            const bool th = act_kind == PJ_ACT_TANH;
-                            if constexpr (P == 4)
-                                *reinterpret_cast<float4*>(zrow + u * RS + p0) =
-                                    make_float4(th ? zq[0][0] : z0s[0], th ? zq[1][0] : z0s[1], th ? zq[2][0] : z0s[2],
-                                                th ? zq[3][0] : z0s[3]);
-                            else
-                                *reinterpret_cast<float2*>(zrow + u * RS + p0) =
-                                    make_float2(th ? zq[0][0] : z0s[0], th ? zq[1][0] : z0s[1]);
-                        }
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            if constexpr (P == 4)
-                                *reinterpret_cast<float4*>(act + u * RS + c * T + p0) =
-                                    make_float4(zq[0][c], zq[1][c], zq[2][c], zq[3][c]);
-                            else
-                                *reinterpret_cast<float2*>(act + u * RS + c * T + p0) = make_float2(zq[0][c], zq[1][c]);
-                        }
+                        finish_unit<P, N1, N2>(zq, act_kind, act + u * RS + p0, T, rec ? zrow + u * RS2 : nullptr, T2);
                     }
                 }
                 bar_compute<NTC>();
@@ -275,47 +307,31 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k1_forward_kernel(const __grid
                 const int rows = n_out * C;
                 for (int e = tid; e < rows * T; e += NT_COMPUTE) {
                     const int pt = e % T, row = e / T, o = row / C, c = row - o * C;
-                    float s = (c == 0) ? bo[o] : 0.0f;
                     const float* ap = act + c * T + pt;
-                    for (int k = 0; k < hpL; ++k) s = fmaf(wl[k * n_out + o], ap[k * RS], s);
-                    ycache[(net.yrow0 + row) * EPI_BATCH + batch_n + pt] = s;
+                    const float* wp = wl + o;
+                    float s0 = (c == 0) ? bo[o] : 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;   // 4 chains: latency, not order
+#pragma unroll 2
+                    for (int k = 0; k < hpL; k += 4) {   // hpL is a multiple of 32
+                        s0 = fmaf(wp[(k + 0) * n_out], ap[(k + 0) * RS], s0);
+                        s1 = fmaf(wp[(k + 1) * n_out], ap[(k + 1) * RS], s1);
+                        s2 = fmaf(wp[(k + 2) * n_out], ap[(k + 2) * RS], s2);
+                        s3 = fmaf(wp[(k + 3) * n_out], ap[(k + 3) * RS], s3);
+                    }
+                    yb[(net.yrow0 + row) * EB + pt] = (s0 + s1) + (s2 + s3);
                 }
             }
             bar_compute<NTC>();
             PJ_T_MARK(5)
         }
 
-        // ---------------- residual program over the collected batch ----------------
-        if (batch_n == 0) batch_first_iter = iter;
-        batch_n += T;
-        if (batch_n + T > EPI_BATCH || iter == my_tiles - 1) {
-            if (tid < batch_n) {
-                const int tl = tid / T, pt = tid - tl * T;
-                const long long btile = (long long)blockIdx.x + (long long)(batch_first_iter + tl) * gridDim.x;
-                const long long gidx = btile * T + pt;
-                float* seed_tile = train ? A.seeds + btile * ((long long)sp.n_yrows * T) + pt : nullptr;
-                if (gidx < A.N) {
-                    ProgIO io{A.coords, gidx, A.N, ycache + tid, A.rbar, A.loss_scale, A.u_out, A.r_out, seed_tile, T};
-                    my_sumsq += run_program<EPI_BATCH>(prog_s, A.prog_len, slots + tid, io);
-                } else if (train) {
-                    for (int r = 0; r < sp.n_yrows; ++r) seed_tile[r * T] = 0.0f;   // padded points: zero adjoint
-                }
-            }
-            batch_n = 0;
-            bar_compute<NTC>();
-            PJ_T_MARK(6)
+        // ---------------- hand a complete batch of raw-output jets to the program warp ----------------
+        if (++bslot == tiles_per_batch || iter == my_tiles - 1) {
+            if (tid == 0) mbar_arrive(&yfull[batch_idx & 1]);   // after the barrier above: every jet of the batch is written
+            ++batch_idx;
+            bslot = 0;
         }
     }
     PJ_T_FLUSH(0)
-
-    my_sumsq = warp_sum(my_sumsq);
-    if (lane == 0) red[warp] = my_sumsq;
-    bar_compute<NTC>();
-    if (tid == 0) {
-        float s = 0.0f;
-        for (int w = 0; w < N_CWARPS; ++w) s += red[w];
-        A.loss_part[blockIdx.x] = s;
-    }
 }
 
 }  // namespace pj

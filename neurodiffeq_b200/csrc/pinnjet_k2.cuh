@@ -17,7 +17,7 @@
 
 namespace pj {
 
-constexpr int WJ = 4, WK = 4;   // weight-gradient output tile per thread
+constexpr int WJ = 8, WK = 4;   // weight-gradient output tile per thread (8 rows of z_bar x 4 rows of a-jets)
 
 // out[j][k] += sum_r G[j][r] * Z[k][r],  r over the C*T (channel, point) pairs; rows interleaved over lanes so that the
 // float4 loads of 8 consecutive rows (stride RS = C*T+4 floats) hit 32 distinct banks.
@@ -246,21 +246,18 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k2_backward_kernel(const __gri
                 // (2c) W_l gradient: out[j][k] += sum_{c,pt} G[j][c,pt] * Zb[k][c,pt]
                 {
                     const int width_j = net.width[h], width_k = net.width[h - 1];   // unpadded
-                    const int n_kb = HK / 32, n_jb = HJ / 16;   // warp tile = 16 rows j x 32 rows k
+                    const int n_kb = HK / 32, n_jb = HJ / 32;   // warp tile = 32 rows j x 32 rows k
                     float* gw = gpart + net.w_off[l];
                     for (int wt = warp; wt < n_kb * n_jb; wt += N_CWARPS) {
-                        const int jb = (wt / n_kb) * 16, kb = (wt % n_kb) * 32;
+                        const int jb = (wt / n_kb) * 32, kb = (wt % n_kb) * 32;
                         f2 wacc[WJ][WK];
-                        float old[WJ][WK];   // running partial of this thread's 4x4 outputs: loads overlap the GEMM
 #pragma unroll
                         for (int i = 0; i < WJ; ++i)
 #pragma unroll
-                            for (int jj = 0; jj < WK; ++jj) {
-                                wacc[i][jj] = 0ull;
-                                const int j = jb + jl + 4 * i, k = kb + kl + 8 * jj;
-                                old[i][jj] = (j < width_j && k < width_k) ? gw[(size_t)j * width_k + k] : 0.0f;
-                            }
+                            for (int jj = 0; jj < WK; ++jj) wacc[i][jj] = 0ull;
                         wgrad_tile(wacc, G + (size_t)(jb + jl) * RS, 4, Zb + (size_t)(kb + kl) * RS, 8, RS, C * T);
+                        // every output element is owned by one thread of this CTA, so the fire-and-forget reduction
+                        // (RED.ADD, no return value to wait for) into the CTA's private partial is race-free and ordered
 #pragma unroll
                         for (int i = 0; i < WJ; ++i) {
                             const int j = jb + jl + 4 * i;
@@ -269,7 +266,7 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k2_backward_kernel(const __gri
                                 const int k = kb + kl + 8 * jj;
                                 if (j < width_j && k < width_k) {
                                     const float2 v = unpack2(wacc[i][jj]);
-                                    gw[(size_t)j * width_k + k] = old[i][jj] + (v.x + v.y);
+                                    atomicAdd(&gw[(size_t)j * width_k + k], v.x + v.y);
                                 }
                             }
                         }

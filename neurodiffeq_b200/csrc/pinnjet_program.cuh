@@ -13,7 +13,8 @@ struct ProgIO {
     const float* const* coords;   // SoA coordinate pointers
     long long gidx;               // global point index
     long long N;
-    const float* ycache;          // jet table of the batch: row * EPI_BATCH + b
+    const float* ycache;          // jet table of the batch: row * ystride + b
+    int ystride;
     const float* rbar;            // [n_eq][N] or nullptr
     float loss_scale;
     float* u_out;                 // [n_funcs][N] or nullptr
@@ -23,7 +24,7 @@ struct ProgIO {
 };
 
 // returns sum of squared residuals of this point
-template <int EPI_BATCH>
+template <int SLOT_STRIDE>
 __device__ __forceinline__ float run_program(const int4* __restrict__ prog, int len, float* __restrict__ slot,
                                              const ProgIO& io) {
     float sumsq = 0.0f;
@@ -33,18 +34,18 @@ __device__ __forceinline__ float run_program(const int4* __restrict__ prog, int 
         const int op = ins.x;
         float v;
         if (op >= OP_ADD && op <= OP_DIV) {
-            const float a = slot[ins.z * EPI_BATCH], b = slot[ins.w * EPI_BATCH];
+            const float a = slot[ins.z * SLOT_STRIDE], b = slot[ins.w * SLOT_STRIDE];
             v = (op == OP_ADD) ? a + b : (op == OP_SUB) ? a - b : (op == OP_MUL) ? a * b : a / b;
         } else if (op <= OP_PARAM) {
             switch (op) {
                 case OP_CONST: v = __int_as_float(ins.z); break;
                 case OP_COORD: v = __ldg(io.coords[ins.z] + io.gidx); break;
-                case OP_NET: v = io.ycache[ins.z * EPI_BATCH]; break;
+                case OP_NET: v = io.ycache[ins.z * io.ystride]; break;
                 case OP_RBAR: v = __ldg(io.rbar + (long long)ins.z * io.N + io.gidx); break;
                 default: v = io.loss_scale; break;
             }
         } else if (op >= OP_ST_U && op <= OP_ST_SEED) {
-            const float a = slot[ins.z * EPI_BATCH];
+            const float a = slot[ins.z * SLOT_STRIDE];
             if (op == OP_ST_U) {
                 if (io.u_out) io.u_out[(long long)ins.y * io.N + io.gidx] = a;
             } else if (op == OP_ST_R) {
@@ -55,7 +56,7 @@ __device__ __forceinline__ float run_program(const int4* __restrict__ prog, int 
             }
             continue;
         } else {
-            const float a = slot[ins.z * EPI_BATCH];
+            const float a = slot[ins.z * SLOT_STRIDE];
             switch (op) {
                 case OP_NEG: v = -a; break;
                 case OP_SIN: v = sinf(a); break;
@@ -75,7 +76,7 @@ __device__ __forceinline__ float run_program(const int4* __restrict__ prog, int 
                 default: v = erff(a); break;
             }
         }
-        slot[ins.y * EPI_BATCH] = v;
+        slot[ins.y * SLOT_STRIDE] = v;
     }
     return sumsq;
 }
