@@ -170,6 +170,30 @@ __device__ __forceinline__ float pg_sum(float v) {
     return v;
 }
 
+// Reduce-scatter over the 8 point-group lanes (recursive halving): every thread contributes 8 (or 4) partial sums, lane l
+// of each 8-lane group returns the total of value l (value l >> 1 for the 4-value form, in both lanes of a pair):
+// 7 (4) shuffles instead of 24 (12) for all-reduce style pg_sum calls.
+__device__ __forceinline__ float pg_reduce_scatter8(const float (&v)[8], int pg_lane) {
+    const bool b2 = pg_lane & 4, b1 = pg_lane & 2, b0 = pg_lane & 1;
+    float w[4], x[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        w[i] = (b2 ? v[i + 4] : v[i]) + __shfl_xor_sync(0xffffffffu, b2 ? v[i] : v[i + 4], 4);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+        x[i] = (b1 ? w[i + 2] : w[i]) + __shfl_xor_sync(0xffffffffu, b1 ? w[i] : w[i + 2], 2);
+    return (b0 ? x[1] : x[0]) + __shfl_xor_sync(0xffffffffu, b0 ? x[0] : x[1], 1);
+}
+__device__ __forceinline__ float pg_reduce_scatter4(const float (&v)[4], int pg_lane) {
+    const bool b2 = pg_lane & 4, b1 = pg_lane & 2;
+    float w[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+        w[i] = (b2 ? v[i + 2] : v[i]) + __shfl_xor_sync(0xffffffffu, b2 ? v[i] : v[i + 2], 4);
+    float x = (b1 ? w[1] : w[0]) + __shfl_xor_sync(0xffffffffu, b1 ? w[0] : w[1], 2);
+    return x + __shfl_xor_sync(0xffffffffu, x, 1);   // value index = pg_lane >> 1
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // activation jets.  Channels: 0 value | 1..N1 first order | N1+1..N1+N2 pure second order.
 // ---------------------------------------------------------------------------------------------------------------------

@@ -123,10 +123,12 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k2_backward_kernel(const __gri
             {
                 const float* wlo = small + pl.s_wlo[n];
                 if (u0 < hpL) {
+                    static_assert(Q == 4, "the gradient reductions below assume 4 units per thread");
+                    float gbq[Q], gwq[PJ_MAX_NETS][Q];   // per-thread partials: bias of hidden L, W_out (n_out <= 4)
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
                         const int u = u0 + q;
-                        float gw[PJ_MAX_NETS];   // n_out <= 4 partial sums of W_out gradient
+                        float gw[PJ_MAX_NETS];
 #pragma unroll
                         for (int o = 0; o < PJ_MAX_NETS; ++o) gw[o] = 0.0f;
                         float gb = 0.0f;
@@ -157,15 +159,26 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k2_backward_kernel(const __gri
 #pragma unroll
                             for (int c = 0; c < C; ++c) G[u * RS + c * T + pt] = zb[c];
                         }
-                        gb = pg_sum(gb);
+                        gbq[q] = gb;
 #pragma unroll
-                        for (int o = 0; o < PJ_MAX_NETS; ++o)
-                            if (o < n_out) gw[o] = pg_sum(gw[o]);
-                        if (jm.pg_lane == 0) {
-                            sg[pl.g_b[n][L - 1] + u] += gb;
-#pragma unroll
-                            for (int o = 0; o < PJ_MAX_NETS; ++o)
-                                if (o < n_out) sg[pl.g_wl[n] + o * hpL + u] += gw[o];
+                        for (int o = 0; o < PJ_MAX_NETS; ++o) gwq[o][q] = gw[o];
+                    }
+                    {   // reduce over the point lanes: [bias(4) | W_out row 0 (4)], then W_out rows 1.. two at a time
+                        const int pl8 = jm.pg_lane, i4 = pl8 & 3;
+                        const float v0[8] = {gbq[0], gbq[1], gbq[2], gbq[3], gwq[0][0], gwq[0][1], gwq[0][2], gwq[0][3]};
+                        const float t0 = pg_reduce_scatter8(v0, pl8);
+                        if (pl8 < 4) sg[pl.g_b[n][L - 1] + u0 + i4] += t0; else sg[pl.g_wl[n] + u0 + i4] += t0;
+                        if (n_out > 1) {
+                            const float v1[8] = {gwq[1][0], gwq[1][1], gwq[1][2], gwq[1][3],
+                                                 gwq[2][0], gwq[2][1], gwq[2][2], gwq[2][3]};
+                            const float t1 = pg_reduce_scatter8(v1, pl8);
+                            if (pl8 < 4) sg[pl.g_wl[n] + hpL + u0 + i4] += t1;
+                            else if (n_out > 2) sg[pl.g_wl[n] + 2 * hpL + u0 + i4] += t1;
+                        }
+                        if (n_out > 3) {
+                            const float v2[4] = {gwq[3][0], gwq[3][1], gwq[3][2], gwq[3][3]};
+                            const float t2 = pg_reduce_scatter4(v2, pl8);
+                            if (!(pl8 & 1)) sg[pl.g_wl[n] + 3 * hpL + u0 + (pl8 >> 1)] += t2;
                         }
                     }
                 }
@@ -209,6 +222,7 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k2_backward_kernel(const __gri
                 PJ_T_MARK(4)
                 // (2b) reverse activation of hidden h-1: Zb z-jets -> a-jets (in place), G2 <- z_bar_{h-1}
                 if (valid) {
+                    float gbq[Q];
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
                         const int u = u0 + q;
@@ -237,9 +251,10 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k2_backward_kernel(const __gri
                                 *reinterpret_cast<float2*>(G2 + u * RS + c * T + p0) = make_float2(zv[0][c], zv[1][c]);
                             }
                         }
-                        gb = pg_sum(gb);
-                        if (jm.pg_lane == 0) sg[pl.g_b[n][h - 2] + u] += gb;
+                        gbq[q] = gb;
                     }
+                    const float tb = pg_reduce_scatter4(gbq, jm.pg_lane);
+                    if (!(jm.pg_lane & 1)) sg[pl.g_b[n][h - 2] + u0 + (jm.pg_lane >> 1)] += tb;
                 }
                 bar_compute<NTC>();
                 PJ_T_MARK(5)
@@ -306,17 +321,27 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k2_backward_kernel(const __gri
 #pragma unroll
                             for (int f = 0; f < N1; ++f) sf[f] += G[u * RS + (1 + f) * T + p0 + p];
                         }
+                        float sv[PJ_MAX_COORDS];
 #pragma unroll
-                        for (int i = 0; i < PJ_MAX_COORDS; ++i)
+                        for (int i = 0; i < PJ_MAX_COORDS; ++i) {
+                            float s = 0.0f;
                             if (i < net.n_in) {
-                                float s = 0.0f;
 #pragma unroll
                                 for (int p = 0; p < P; ++p) s = fmaf(s0[p], x[i][p], s);
 #pragma unroll
                                 for (int f = 0; f < N1; ++f) s = fmaf(sf[f], sp.dir[f][net.in_coord[i]], s);
-                                s = pg_sum(s);
-                                if (jm.pg_lane == 0) sg[pl.g_w0[n] + u * net.n_in + i] += s;
                             }
+                            sv[i] = s;
+                        }
+                        if (net.n_in <= 4) {
+                            const float v4[4] = {sv[0], sv[1], sv[2], sv[3]};
+                            const float t = pg_reduce_scatter4(v4, jm.pg_lane);
+                            const int i = jm.pg_lane >> 1;
+                            if (!(jm.pg_lane & 1) && i < net.n_in) sg[pl.g_w0[n] + u * net.n_in + i] += t;
+                        } else {
+                            const float t = pg_reduce_scatter8(sv, jm.pg_lane);
+                            if (jm.pg_lane < net.n_in) sg[pl.g_w0[n] + u * net.n_in + jm.pg_lane] += t;
+                        }
                     }
                 }
             }
