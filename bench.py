@@ -236,18 +236,24 @@ def main():
     torch.cuda.synchronize()
 
     graph = None
-    if not args.no_graph and world == 1:
-        graph = torch.cuda.CUDAGraph()
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            step_body()
-        torch.cuda.current_stream().wait_stream(s)
-        with torch.cuda.graph(graph):
-            step_body()
-        for _ in range(3):
-            graph.replay()
-        torch.cuda.synchronize()
+    if not args.no_graph:   # the whole step (fill, K0..K2b and, for N > 1, the NCCL all-reduce) as one CUDA graph
+        try:
+            graph = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                step_body()
+            torch.cuda.current_stream().wait_stream(s)
+            with torch.cuda.graph(graph):
+                step_body()
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+        except Exception as exc:   # noqa: BLE001  (e.g. a NCCL build that cannot be captured): time eager launches
+            print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); timing eager launches",
+                  file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
 
     def run_step():
         if graph is not None:
@@ -317,9 +323,10 @@ def main():
 
     # ---- e2e: host coordinates in, loss out, through the public call -------------------------------------------------
     def e2e_step():
-        dev_coords = [h.to(dev, non_blocking=True) for h in host_coords]
+        # the public call: host coordinates in (staged through pinned buffers, H2D inside), CUDA-graph replay of
+        # K0..K2b, loss read back to the host
         fp.gradbuf.zero_()
-        fp.residual_grad(dev_coords, n_global=n_global, sumsq_out=fp.sumsq)
+        fp.residual_grad_graphed(host_coords, n_global=n_global)
         if world > 1:
             dist.all_reduce(fp.gradbuf)
         return fp.sumsq.item()   # device -> host read of the step's result
@@ -352,9 +359,14 @@ def main():
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
     fp32_peak = n_sms * 128 * 2 * sm_mhz * 1e6 / 1e12       # FFMA lanes x 2 flop x clock under load
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01", "traffic.json")   # dram__bytes_read+write of K1 from `ncu --set full`
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {}).get("k1_dram_bytes")
     roofline = {
         "kernel": "k1_forward_kernel (forward + jets + residual program)", "bound": "tensor", "achieved": ach_k1,
-        "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach_k1 / bf16_peak, "traffic": None,
+        "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach_k1 / bf16_peak, "traffic": traffic,
         "peak_source": f"dense bf16 tensor, {peak_src}",
         "pipe": "fp32 FFMA2 on CUDA cores (fp32 parity; tensor cores would need 3xTF32 split, see DESIGN.md)",
         "fp32_ffma_peak": fp32_peak, "frac_of_fp32_ffma_peak": ach_k1 / fp32_peak,

@@ -121,6 +121,7 @@ class FusedProblem:
         self.workspace = None
         self._ws_points = 0
         self.kernel_launches = 0
+        self._graphs = {}
 
     # ---- parameters: one flat fp32 buffer, nn.Parameters become views (torch layout preserved) ----------------------
     def _adopt_parameters(self):
@@ -227,6 +228,7 @@ class FusedProblem:
         need = sz.workspace_bytes if train else 4096
         if self.workspace is None or self.workspace.numel() < need:
             self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._graphs.clear()          # captured graphs hold the old workspace pointer
         return sz
 
     @staticmethod
@@ -323,6 +325,57 @@ class FusedProblem:
             info["zj_off"].append([int(out[k + i]) for i in range(PJ_MAX_LINEAR)])
             k += PJ_MAX_LINEAR
         return info
+
+    # ---- CUDA-graph replay of a whole residual+gradient evaluation -----------------------------------------------------
+    def _graph_state(self, n, n_global, train):
+        key = (int(n), int(n_global), bool(train))
+        st = self._graphs.get(key)
+        if st is not None:
+            return st
+        dev = self.device
+        static = [torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(self.n_coords)]
+        pinned = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(self.n_coords)]
+
+        def body():
+            if train:
+                self.residual_grad(static, n_global=n_global, sumsq_out=self.sumsq)
+            else:
+                self.forward(static, want_u=False, want_residual=False, want_sumsq=True)
+
+        keep = self.gradbuf.clone()          # warm-up (sizes buffers, sets kernel attributes) must not leak into grads
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+        torch.cuda.synchronize(dev)
+        self.gradbuf.copy_(keep)
+        st = (graph, static, pinned)
+        self._graphs[key] = st
+        return st
+
+    def residual_grad_graphed(self, coords, n_global=None, train=True):
+        """Same contract as :meth:`residual_grad` with ``sumsq_out=self.sumsq`` (``grad`` and ``sumsq`` ACCUMULATE; zero
+        ``gradbuf`` yourself), but K0+K1+finalize+K2+K2b are replayed from a CUDA graph captured once per batch size.
+        ``coords`` may be host tensors (staged through persistent pinned buffers) or device tensors.
+        ``train=False`` replays the validation path (sum of squared residuals only)."""
+        n = coords[0].numel()
+        graph, static, pinned = self._graph_state(n, n if n_global is None else n_global, train)
+        for dst, pin, src in zip(static, pinned, coords):
+            src = src.detach().reshape(-1)
+            if src.device.type != "cpu":
+                dst.copy_(src)
+            elif src.is_pinned() and src.dtype == torch.float32 and src.is_contiguous():
+                dst.copy_(src, non_blocking=True)     # already page-locked: DMA straight from the caller's buffer
+            else:                                     # single-threaded host copy (+ dtype conversion) into the pinned
+                np.copyto(pin.numpy(), src.numpy(), casting="same_kind")   # stage: torch's parallel CPU copy costs
+                dst.copy_(pin, non_blocking=True)                          # milliseconds on many-core hosts
+        graph.replay()
+        self.kernel_launches += 5 if train else 3
+        return self.sumsq
 
     # ---- debugging / tests: raw views of the workspace -----------------------------------------------------------------
     def flat_params_numpy(self):

@@ -202,22 +202,23 @@ class BaseSolver:
 
     # ---- batches ------------------------------------------------------------------------------------------------------
     def _generate_batch(self, key):
+        """Host sampling (stays on the host, north_star).  Returns flat float32 columns, still wherever the generator put
+        them (normally the CPU); the engine stages them to the device."""
         self._phase = key
-        cols = self.generator[key].get_examples()
-        dev = [c.detach().reshape(-1).to(torch.float32).contiguous() for c in cols]
-        if any(c.device != self.device for c in dev):
-            dev = [c.pin_memory().to(self.device, non_blocking=True) if c.device.type == "cpu" else c.to(self.device)
-                   for c in dev]
+        cols = [c.detach().reshape(-1) for c in self.generator[key].get_examples()]
         if self._dist is not None:  # every rank samples the same batch (same seed) and keeps its slice
             w, r = self._dist.get_world_size(), self._dist.get_rank()
-            n = dev[0].numel()
+            n = cols[0].numel()
             lo, hi = shard_bounds(n, r, w)
             self._n_global = n
-            dev = [c[lo:hi].contiguous() for c in dev]
+            cols = [c[lo:hi] for c in cols]
         else:
-            self._n_global = dev[0].numel()
-        self._batch[key] = [c.reshape(-1, 1) for c in dev]
-        return dev
+            self._n_global = cols[0].numel()
+        self._batch[key] = [c.reshape(-1, 1) for c in cols]
+        return cols
+
+    def _to_device(self, cols):
+        return [c.to(self.device, torch.float32, non_blocking=True).contiguous() for c in cols]
 
     def _update_history(self, value, metric_type, key):
         self._phase = key
@@ -256,15 +257,17 @@ class BaseSolver:
         for _ in range(n_b):
             coords = self._generate_batch(key)
             denom = float(self._n_global * fp.n_eq)          # loss of a batch = mean over its N_global * n_eq entries
-            cols = [c.reshape(-1, 1) for c in coords]
             if self._custom_loss is None:
+                # fused mean-squared residual: the whole batch (K0..K2b) is one CUDA-graph replay; gradients of the
+                # batches ADD UP (no averaging), like repeated loss.backward()
                 fp.sumsq.zero_()
-                if key == "train":   # gradients of the batches ADD UP (no averaging), like repeated loss.backward()
-                    fp.residual_grad(coords, n_global=self._n_global, sumsq_out=fp.sumsq, repack=False)
-                else:
-                    fp.forward(coords, want_u=False, want_residual=False, want_sumsq=True, repack=False)
+                fp.residual_grad_graphed(coords, n_global=self._n_global, train=(key == "train"))
                 loss_acc += fp.sumsq / denom
+                if self.metrics_fn:
+                    coords = self._to_device(coords)
             else:
+                coords = self._to_device(coords)
+                cols = [c.reshape(-1, 1) for c in coords]
                 u, r, _ = fp.forward(coords, want_u=True, want_residual=True, repack=False)
                 res = r.t().contiguous().requires_grad_(key == "train")      # (N, n_eq) like torch.cat(residuals, 1)
                 funcs = [u[k].reshape(-1, 1) for k in range(u.shape[0])]
