@@ -400,9 +400,15 @@ def main():
             "step_ms_stats": {"min": float(step_ms.min()), "median": float(np.median(step_ms)),
                               "max": float(step_ms.max())},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing down a process group whose all-reduce was captured in a CUDA graph can block for minutes inside NCCL
+        # (seen on 2 GPUs).  Every rank is done once rank 0 has printed: synchronise and leave without the teardown.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
