@@ -297,7 +297,7 @@ def main():
     scale = ctypes.c_float(2.0 / (n_global * fp.n_eq))
 
     def k1_only():
-        E._check(fp.lib.pj_forward_train(sp, fp.prog_train.data_ptr(), len(fp.tp.prog_train), ptrs, n,
+        E._check(fp.lib.pj_forward_train(sp, fp.prog_train.data_ptr(), len(fp.tp.prog_train), *fp._prog_w_args(), ptrs, n,
                                          fp.pack_buf.data_ptr(), scale, None, None, None, fp.workspace.data_ptr(),
                                          fp.workspace.numel(), cs()), "k1")
 
@@ -371,6 +371,11 @@ def main():
         "pipe": "fp32 FFMA2 on CUDA cores (fp32 parity; tensor cores would need 3xTF32 split, see DESIGN.md)",
         "fp32_ffma_peak": fp32_peak, "frac_of_fp32_ffma_peak": ach_k1 / fp32_peak,
         "algorithmic_flops_per_point": wl.flops_fwdjet, "launch_ms": k1_ms, "launch_ms_min": k1_min,
+        # `achieved` counts the CANONICAL jet FLOPs (one channel per needed partial derivative).  When the
+        # tracer proves the residual affine in the pure second derivatives, the kernels carry ONE weighted second-order
+        # channel instead (forward-Laplacian): fewer channels are executed for the same result.
+        "channels_canonical": 1 + fp.tp.scheme.n1 + fp.tp.scheme.n2, "channels_executed": fp.tp.n_channels,
+        "executed_flops_per_point": int(round(wl.flops_fwdjet * fp.tp.n_channels / (1 + fp.tp.scheme.n1 + fp.tp.scheme.n2))),
         "k2": {"kernel": "k2_backward_kernel + k2_reduce_kernel", "algorithmic_flops_per_point": 2 * wl.flops_fwdjet,
                "launch_ms": k2_ms, "achieved": 2 * flops_k1 / (k2_ms * 1e-3) / 1e12,
                "frac_of_fp32_ffma_peak": 2 * flops_k1 / (k2_ms * 1e-3) / 1e12 / fp32_peak},

@@ -20,6 +20,8 @@
  *   u_out       : float[n_funcs][N]   re-parameterised functions  (conditions.py:41-57)
  *   resid_out   : float[n_eq][N]      residuals of diff_eqs       (solvers.py:380-381, transposed: SoA)
  *   program     : int32[len][4] bytecode produced by neurodiffeq_b200/symbolic.py (op,dst,a,b)
+ *   prog_w      : optional weight program (coords -> wl weights per net) of the combined second-order channel; NULL/0
+ *                 when spec->wl == 0
  */
 #ifndef PINNJET_H
 #define PINNJET_H
@@ -31,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PJ_ABI_VERSION 1
+#define PJ_ABI_VERSION 2
 #define PJ_MAX_NETS 4
 #define PJ_MAX_LINEAR 8   /* nn.Linear layers per network (hidden layers + 1) */
 #define PJ_MAX_COORDS 8
@@ -57,7 +59,10 @@ typedef struct PjSpec {
     int32_t abi_version;                /* PJ_ABI_VERSION                                                     */
     int32_t n_coords;                   /* number of sampled coordinates (d0)                                 */
     int32_t n_nets;                     /* distinct networks                                                  */
-    int32_t n1, n2;                     /* jet channels: value | n1 directional firsts | n2 pure seconds      */
+    int32_t n1, n2;                     /* jet channels: value | n1 directional firsts | n2 second-order      */
+    int32_t wl;                         /* 0: the n2 channels are pure seconds of the first n2 directions;    */
+                                        /* >0: n2 == 1 and the channel is L = sum_{d<wl} w_d(x) D_d^2 with    */
+                                        /* per-point weights produced by the weight program (prog_w)          */
     float dir[PJ_MAX_DIRS][PJ_MAX_COORDS]; /* direction vectors of the first-order channels (coordinate space) */
     int32_t n_funcs, n_eq;              /* outputs of the eval program                                        */
     int32_t n_yrows;                    /* rows of the jet table = sum_n n_out(n) * C                         */
@@ -96,6 +101,7 @@ int pj_pack(const PjSpec* spec, const float* theta /*device*/, float* theta_pack
  *           (solvers.py:373-381, get_residuals :606-646, BaseSolution.__call__ :682-720).
  * u_out / resid_out / sumsq_out may be NULL.  *sumsq_out += sum over points and equations of r^2.            */
 int pj_forward(const PjSpec* spec, const int32_t* prog_eval /*device*/, int32_t prog_len,
+               const int32_t* prog_w /*device or NULL*/, int32_t prog_w_len,
                const float* const* coords /*host array of device ptrs*/, int64_t n_points,
                const float* theta_pack /*device*/, float* u_out, float* resid_out, float* sumsq_out,
                void* workspace /*device*/, size_t workspace_bytes, void* stream);
@@ -105,6 +111,7 @@ int pj_forward(const PjSpec* spec, const int32_t* prog_eval /*device*/, int32_t 
  * If rbar != NULL it is float[n_eq][N] = dL/dr supplied by the caller (custom loss_fn, solvers.py:216-226) and the
  * program must be the external-cotangent variant.  resid_out may be NULL.  *sumsq_out += sum r^2.             */
 int pj_forward_train(const PjSpec* spec, const int32_t* prog_train /*device*/, int32_t prog_len,
+                     const int32_t* prog_w /*device or NULL*/, int32_t prog_w_len,
                      const float* const* coords, int64_t n_points, const float* theta_pack,
                      float loss_scale, const float* rbar, float* resid_out, float* sumsq_out,
                      void* workspace, size_t workspace_bytes, void* stream);

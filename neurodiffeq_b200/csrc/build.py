@@ -8,7 +8,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SCHEMES = [(1, 0), (1, 1), (2, 0), (2, 1), (2, 2), (3, 0), (3, 3)]
+SCHEMES = [(1, 0, 0), (1, 1, 0), (2, 0, 0), (2, 1, 0), (2, 2, 0), (3, 0, 0), (3, 3, 0), (2, 1, 2), (3, 1, 3)]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -44,9 +44,9 @@ def build(force=False, verbose=False, extra_flags=(), lib=None, objdir_name="bui
     jobs = [(os.path.join(objdir, "api.o"), os.path.join(HERE, "pinnjet_api.cu"), list(extra_flags)),
             (os.path.join(objdir, "inst_common.o"), os.path.join(HERE, "pinnjet_inst.cu"),
              ["-DPJ_N1=-1", "-DPJ_N2=-1"] + list(extra_flags))]
-    for n1, n2 in SCHEMES:
-        jobs.append((os.path.join(objdir, f"inst_{n1}_{n2}.o"), os.path.join(HERE, "pinnjet_inst.cu"),
-                     [f"-DPJ_N1={n1}", f"-DPJ_N2={n2}"] + list(extra_flags)))
+    for n1, n2, wl in SCHEMES:
+        jobs.append((os.path.join(objdir, f"inst_{n1}_{n2}_{wl}.o"), os.path.join(HERE, "pinnjet_inst.cu"),
+                     [f"-DPJ_N1={n1}", f"-DPJ_N2={n2}", f"-DPJ_WL={wl}"] + list(extra_flags)))
     logs = []
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         for out, rc, log in ex.map(_compile, jobs):

@@ -8,17 +8,19 @@
 namespace pj {
 
 // per-scheme launchers, defined in pinnjet_inst.cu (one translation unit per jet-channel scheme)
-#define PJ_DECL(N1, N2)                                                                  \
-    cudaError_t launch_k1_##N1##_##N2(const K1Args& a, int grid, int smem, cudaStream_t s); \
-    cudaError_t launch_k2_##N1##_##N2(const K2Args& a, int grid, int smem, cudaStream_t s); \
-    int occupancy_##N1##_##N2(int which, int ntc, int smem);
-PJ_DECL(1, 0)
-PJ_DECL(1, 1)
-PJ_DECL(2, 0)
-PJ_DECL(2, 1)
-PJ_DECL(2, 2)
-PJ_DECL(3, 0)
-PJ_DECL(3, 3)
+#define PJ_DECL(N1, N2, WL)                                                                        \
+    cudaError_t launch_k1_##N1##_##N2##_##WL(const K1Args& a, int grid, int smem, cudaStream_t s); \
+    cudaError_t launch_k2_##N1##_##N2##_##WL(const K2Args& a, int grid, int smem, cudaStream_t s); \
+    int occupancy_##N1##_##N2##_##WL(int which, int ntc, int smem);
+PJ_DECL(1, 0, 0)
+PJ_DECL(1, 1, 0)
+PJ_DECL(2, 0, 0)
+PJ_DECL(2, 1, 0)
+PJ_DECL(2, 2, 0)
+PJ_DECL(3, 0, 0)
+PJ_DECL(3, 3, 0)
+PJ_DECL(2, 1, 2)   // combined second-order channel over 2 / 3 weighted directions
+PJ_DECL(3, 1, 3)
 #undef PJ_DECL
 cudaError_t launch_reduce(const float* gpart, int n_parts, long long n_theta, float* grad, cudaStream_t s);
 cudaError_t launch_loss_finalize(const float* part, int n_parts, float* out, cudaStream_t s);
@@ -26,15 +28,16 @@ cudaError_t launch_loss_finalize(const float* part, int n_parts, float* out, cud
 typedef cudaError_t (*K1Launch)(const K1Args&, int, int, cudaStream_t);
 typedef cudaError_t (*K2Launch)(const K2Args&, int, int, cudaStream_t);
 struct SchemeEntry {
-    int n1, n2;
+    int n1, n2, wl;
     K1Launch k1;
     K2Launch k2;
     int (*occ)(int, int, int);
 };
 static const SchemeEntry kSchemes[] = {
-    {1, 0, launch_k1_1_0, launch_k2_1_0, occupancy_1_0}, {1, 1, launch_k1_1_1, launch_k2_1_1, occupancy_1_1}, {2, 0, launch_k1_2_0, launch_k2_2_0, occupancy_2_0},
-    {2, 1, launch_k1_2_1, launch_k2_2_1, occupancy_2_1}, {2, 2, launch_k1_2_2, launch_k2_2_2, occupancy_2_2}, {3, 0, launch_k1_3_0, launch_k2_3_0, occupancy_3_0},
-    {3, 3, launch_k1_3_3, launch_k2_3_3, occupancy_3_3},
+    {1, 0, 0, launch_k1_1_0_0, launch_k2_1_0_0, occupancy_1_0_0}, {1, 1, 0, launch_k1_1_1_0, launch_k2_1_1_0, occupancy_1_1_0}, {2, 0, 0, launch_k1_2_0_0, launch_k2_2_0_0, occupancy_2_0_0},
+    {2, 1, 0, launch_k1_2_1_0, launch_k2_2_1_0, occupancy_2_1_0}, {2, 2, 0, launch_k1_2_2_0, launch_k2_2_2_0, occupancy_2_2_0}, {3, 0, 0, launch_k1_3_0_0, launch_k2_3_0_0, occupancy_3_0_0},
+    {3, 3, 0, launch_k1_3_3_0, launch_k2_3_3_0, occupancy_3_3_0},
+    {2, 1, 2, launch_k1_2_1_2, launch_k2_2_1_2, occupancy_2_1_2}, {3, 1, 3, launch_k1_3_1_3, launch_k2_3_1_3, occupancy_3_1_3},
 };
 
 static thread_local char g_err[512] = "";
@@ -46,9 +49,9 @@ static int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-static const SchemeEntry* find_scheme(int n1, int n2) {
+static const SchemeEntry* find_scheme(int n1, int n2, int wl) {
     for (const auto& e : kSchemes)
-        if (e.n1 == n1 && e.n2 == n2) return &e;
+        if (e.n1 == n1 && e.n2 == n2 && e.wl == wl) return &e;
     return nullptr;
 }
 
@@ -76,16 +79,17 @@ static int pick_stages(int fixed_bytes, int chunks, int target_occ, bool residen
 }
 
 // Everything the kernels need to agree on.  prog_len only moves the end of the K1 shared-memory image.
-static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int ntc_req, Plan& pl, int* occ_min) {
+static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w_len, int ntc_req, Plan& pl, int* occ_min) {
     memset(&pl, 0, sizeof(pl));
     if (sp.abi_version != PJ_ABI_VERSION) return fail(-1, "PjSpec.abi_version %d != %d", sp.abi_version, PJ_ABI_VERSION);
     if (sp.n_nets < 1 || sp.n_nets > PJ_MAX_NETS) return fail(-1, "n_nets=%d out of range", sp.n_nets);
     if (sp.n_coords < 1 || sp.n_coords > PJ_MAX_COORDS) return fail(-1, "n_coords=%d out of range", sp.n_coords);
-    if (!find_scheme(sp.n1, sp.n2))
-        return fail(-2, "jet channel scheme (n1=%d, n2=%d) has no compiled kernel", sp.n1, sp.n2);
+    if (!find_scheme(sp.n1, sp.n2, sp.wl))
+        return fail(-2, "jet channel scheme (n1=%d, n2=%d, wl=%d) has no compiled kernel", sp.n1, sp.n2, sp.wl);
     if (N < 1) return fail(-1, "n_points must be positive");
     if (prog_len > PROG_MAX) return fail(-2, "residual program too long (%d > %d instructions)", prog_len, PROG_MAX);
     if (sp.n_slots < 1 || sp.n_slots > 64) return fail(-2, "n_slots=%d out of range (1..64)", sp.n_slots);
+    if (sp.wl < 0 || sp.wl > sp.n1 || (sp.wl > 0 && sp.n2 != 1)) return fail(-1, "inconsistent wl=%d (n1=%d, n2=%d)", sp.wl, sp.n1, sp.n2);
     const int C = 1 + sp.n1 + sp.n2;
     pl.C = C;
     if (C <= 2) { pl.P = 4; pl.Q = 4; } else { pl.P = 2; pl.Q = 4; }
@@ -186,8 +190,10 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int ntc_re
     {   // K1: act | ring | small | ycache | slots | misc | prog
         const int act_bytes = hmax * pl.RS1 * 4;
         const int ycache_bytes = 2 * sp.n_yrows * pl.epi_batch * 4, slots_bytes = sp.n_slots * 32 * 4;
-        const int fixed = act_bytes + small_bytes + ycache_bytes + slots_bytes + misc_bytes +
-                          prog_len * 16;
+        const int nw = sp.n_nets * sp.wl;
+        const int wbuf_bytes = nw * pl.T1 * 4, wslots_bytes = sp.wl > 0 ? sp.n_slots * pl.ntc1 * 4 : 0;
+        const int fixed = act_bytes + small_bytes + ycache_bytes + slots_bytes + misc_bytes + wbuf_bytes + wslots_bytes +
+                          (prog_len + prog_w_len) * 16;
         // 128-thread forward CTAs share one service warp between weight loading and the residual program -> resident only
         const int ns = pick_stages(fixed, pl.chunks_fwd, pl.ntc1 == 128 ? 3 : 1, pl.ntc1 == 128);
         if (ns < 0) return fail(-2, "forward kernel does not fit in shared memory");
@@ -200,7 +206,10 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int ntc_re
         pl.k1_ycache = o; o += ycache_bytes;
         pl.k1_slots = o; o += slots_bytes;
         pl.k1_misc = o; o += misc_bytes;
+        pl.k1_wbuf = o; o += wbuf_bytes;
+        pl.k1_wslots = o; o += wslots_bytes;
         pl.k1_prog = o; o += prog_len * 16;
+        pl.k1_progw = o; o += prog_w_len * 16;
         pl.k1_bytes = o;
     }
     {   // K2: G | G2 | Zb | ring | small | ybar | sgrad | misc
@@ -225,7 +234,7 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int ntc_re
     }
     // ---- persistent grids: resident CTAs per SM x SMs, capped by the number of tiles ----
     {
-        const SchemeEntry* e = find_scheme(sp.n1, sp.n2);
+        const SchemeEntry* e = find_scheme(sp.n1, sp.n2, sp.wl);
         const int o1 = e->occ((pl.ntc1 == 256 && pl.Q1 == 4) ? 3 : 1, pl.ntc1, pl.k1_bytes), o2 = e->occ(2, pl.ntc, pl.k2_bytes);
         if (o1 < 1 || o2 < 1) return fail(-2, "kernel does not fit on an SM (occupancy %d / %d, smem %d / %d B)", o1, o2,
                                           pl.k1_bytes, pl.k2_bytes);
@@ -243,23 +252,24 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int ntc_re
     pl.ws_zj = LOSS_PART_BYTES;
     pl.ws_seed = round_up_ll(pl.ws_zj + 4ll * zt * pl.n_tiles, 256);
     pl.ws_gpart = round_up_ll(pl.ws_seed + 4ll * sp.n_yrows * pl.T * pl.n_tiles, 256);
-    pl.ws_bytes = round_up_ll(pl.ws_gpart + 4ll * sp.n_theta * pl.grid_bwd, 256);
+    pl.ws_wts = round_up_ll(pl.ws_gpart + 4ll * sp.n_theta * pl.grid_bwd, 256);
+    pl.ws_bytes = round_up_ll(pl.ws_wts + 4ll * sp.n_nets * sp.wl * pl.T * pl.n_tiles, 256);
 
     return 0;
 }
 
 // Narrow networks (hidden width <= 64) run 128-thread CTAs when at least two of them fit on an SM in BOTH kernels (their
 // GEMM / activation / program phases then overlap); otherwise one 256-thread CTA per SM.
-static int make_plan(const PjSpec& sp, long long N, int prog_len, Plan& pl) {
+static int make_plan(const PjSpec& sp, long long N, int prog_len, Plan& pl, int prog_w_len = 0) {
     int occ = 0, hmax = 0;
     for (int n = 0; n < sp.n_nets && n < PJ_MAX_NETS; ++n)
         for (int h = 1; h < sp.net[n].n_linear && h <= PJ_MAX_LINEAR; ++h)
             if (sp.net[n].width[h] > hmax) hmax = sp.net[n].width[h];
     if (hmax <= 64) {
-        const int rc = make_plan_ntc(sp, N, prog_len, 128, pl, &occ);
+        const int rc = make_plan_ntc(sp, N, prog_len, prog_w_len, 128, pl, &occ);
         if (rc == 0 && occ >= 2) return 0;
     }
-    return make_plan_ntc(sp, N, prog_len, 256, pl, &occ);
+    return make_plan_ntc(sp, N, prog_len, prog_w_len, 256, pl, &occ);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -383,14 +393,17 @@ int pj_pack(const PjSpec* spec, const float* theta, float* theta_pack, void* str
     return check_cuda(cudaGetLastError(), "pack launch");
 }
 
-static int run_k1(const PjSpec* spec, const int32_t* prog, int32_t prog_len, const float* const* coords, int64_t n,
+static int run_k1(const PjSpec* spec, const int32_t* prog, int32_t prog_len, const int32_t* prog_w, int32_t prog_w_len,
+                  const float* const* coords, int64_t n,
                   const float* theta_pack, int mode, float loss_scale, const float* rbar, float* u_out, float* r_out,
                   float* sumsq_out, void* ws, size_t ws_bytes, void* stream) {
     if (!spec || !prog || !coords || !theta_pack || !ws) return fail(-1, "null argument");
     K1Args a;
     memset(&a, 0, sizeof(a));
     a.spec = *spec;
-    if (int rc = make_plan(*spec, n, prog_len, a.plan)) return rc;
+    if (spec->wl > 0 && (!prog_w || prog_w_len < 1)) return fail(-1, "spec->wl=%d needs a weight program", spec->wl);
+    if (spec->wl == 0) prog_w_len = 0;
+    if (int rc = make_plan(*spec, n, prog_len, a.plan, prog_w_len)) return rc;
     const size_t need = mode == 1 ? (size_t)a.plan.ws_bytes : (size_t)LOSS_PART_BYTES;
     if (ws_bytes < need) return fail(-1, "workspace too small: %zu < %zu bytes", ws_bytes, need);
     if (a.plan.k1_bytes > SMEM_LIMIT) return fail(-2, "forward kernel needs %d B of shared memory", a.plan.k1_bytes);
@@ -401,6 +414,8 @@ static int run_k1(const PjSpec* spec, const int32_t* prog, int32_t prog_len, con
     a.pack = theta_pack;
     a.prog = reinterpret_cast<const int4*>(prog);
     a.prog_len = prog_len;
+    a.prog_w = reinterpret_cast<const int4*>(prog_w);
+    a.prog_w_len = prog_w_len;
     a.mode = mode;
     a.N = n;
     a.loss_scale = loss_scale;
@@ -412,24 +427,26 @@ static int run_k1(const PjSpec* spec, const int32_t* prog, int32_t prog_len, con
     a.dbg = a.loss_part + 640;   // tail of the 4 KB loss-partial block (only written by PJ_TIMING builds)
     a.zj = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_zj) : nullptr;
     a.seeds = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_seed) : nullptr;
-    const SchemeEntry* e = find_scheme(spec->n1, spec->n2);
+    a.wts = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_wts) : nullptr;
+    const SchemeEntry* e = find_scheme(spec->n1, spec->n2, spec->wl);
     if (int rc = check_cuda(e->k1(a, a.plan.grid, a.plan.k1_bytes, (cudaStream_t)stream), "forward launch")) return rc;
     if (sumsq_out)
         return check_cuda(launch_loss_finalize(a.loss_part, a.plan.grid, sumsq_out, (cudaStream_t)stream), "loss finalize");
     return 0;
 }
 
-int pj_forward(const PjSpec* spec, const int32_t* prog_eval, int32_t prog_len, const float* const* coords,
-               int64_t n_points, const float* theta_pack, float* u_out, float* resid_out, float* sumsq_out,
-               void* workspace, size_t workspace_bytes, void* stream) {
-    return run_k1(spec, prog_eval, prog_len, coords, n_points, theta_pack, 0, 0.0f, nullptr, u_out, resid_out, sumsq_out,
+int pj_forward(const PjSpec* spec, const int32_t* prog_eval, int32_t prog_len, const int32_t* prog_w, int32_t prog_w_len,
+               const float* const* coords, int64_t n_points, const float* theta_pack, float* u_out, float* resid_out,
+               float* sumsq_out, void* workspace, size_t workspace_bytes, void* stream) {
+    return run_k1(spec, prog_eval, prog_len, prog_w, prog_w_len, coords, n_points, theta_pack, 0, 0.0f, nullptr, u_out, resid_out, sumsq_out,
                   workspace, workspace_bytes, stream);
 }
 
-int pj_forward_train(const PjSpec* spec, const int32_t* prog_train, int32_t prog_len, const float* const* coords,
-                     int64_t n_points, const float* theta_pack, float loss_scale, const float* rbar, float* resid_out,
-                     float* sumsq_out, void* workspace, size_t workspace_bytes, void* stream) {
-    return run_k1(spec, prog_train, prog_len, coords, n_points, theta_pack, 1, loss_scale, rbar, nullptr, resid_out,
+int pj_forward_train(const PjSpec* spec, const int32_t* prog_train, int32_t prog_len, const int32_t* prog_w,
+                     int32_t prog_w_len, const float* const* coords, int64_t n_points, const float* theta_pack,
+                     float loss_scale, const float* rbar, float* resid_out, float* sumsq_out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    return run_k1(spec, prog_train, prog_len, prog_w, prog_w_len, coords, n_points, theta_pack, 1, loss_scale, rbar, nullptr, resid_out,
                   sumsq_out, workspace, workspace_bytes, stream);
 }
 
@@ -450,8 +467,9 @@ int pj_backward(const PjSpec* spec, const float* const* coords, int64_t n_points
     a.zj = reinterpret_cast<const float*>(w + a.plan.ws_zj);
     a.seeds = reinterpret_cast<const float*>(w + a.plan.ws_seed);
     a.gpart = reinterpret_cast<float*>(w + a.plan.ws_gpart);
+    a.wts = reinterpret_cast<const float*>(w + a.plan.ws_wts);
     a.dbg = reinterpret_cast<float*>(w + a.plan.ws_loss) + 640;
-    const SchemeEntry* e = find_scheme(spec->n1, spec->n2);
+    const SchemeEntry* e = find_scheme(spec->n1, spec->n2, spec->wl);
     if (int rc = check_cuda(e->k2(a, a.plan.grid_bwd, a.plan.k2_bytes, (cudaStream_t)stream), "backward launch")) return rc;
     return check_cuda(launch_reduce(a.gpart, a.plan.grid_bwd, spec->n_theta, grad_theta, (cudaStream_t)stream), "reduce launch");
 }

@@ -29,7 +29,7 @@ constexpr int ROW_PAD = 4;               // jet rows are C*T + 4 floats: conflic
 enum : int {
     OP_CONST = 0, OP_COORD, OP_NET, OP_RBAR, OP_PARAM, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_SIN, OP_COS, OP_EXP,
     OP_LOG, OP_TANH, OP_SQRT, OP_ABS, OP_SIGN, OP_POWC, OP_RCP, OP_ST_U, OP_ST_R, OP_ST_SEED, OP_TAN, OP_SINH, OP_COSH,
-    OP_ATAN, OP_ERF
+    OP_ATAN, OP_ERF, OP_ST_W
 };
 
 // Everything derived from (spec, N): identical on host and device, computed by make_plan() in pinnjet_api.cu.
@@ -61,6 +61,8 @@ struct Plan {
     long long ws_zj, ws_seed, ws_gpart, ws_loss, ws_bytes;
     // ---- shared memory (byte offsets) ----
     int k1_act, k1_ring, k1_small, k1_ycache, k1_slots, k1_prog, k1_misc, k1_bytes;
+    int k1_wbuf, k1_wslots, k1_progw;    // combined second-order channel: per-point weights, their interpreter state
+    long long ws_wts;                    // workspace: weights [tile][n_nets*wl][T] for K2
     int k2_g0, k2_g1, k2_zb, k2_ring, k2_small, k2_ybar, k2_sgrad, k2_misc, k2_bytes;
 };
 
@@ -71,6 +73,8 @@ struct K1Args {
     const float* pack;
     const int4* prog;
     int prog_len;
+    const int4* prog_w;
+    int prog_w_len;
     int mode;                            // 0 = eval (u, residual), 1 = train (residual, seeds, z-jets)
     long long N;
     float loss_scale;
@@ -79,6 +83,7 @@ struct K1Args {
     float* r_out;
     float* zj;
     float* seeds;
+    float* wts;
     float* loss_part;
     float* dbg;                          // diagnostic builds only (PJ_TIMING): phase cycle counters
 };
@@ -91,6 +96,7 @@ struct K2Args {
     long long N;
     const float* zj;
     const float* seeds;
+    const float* wts;
     float* gpart;
     float* dbg;
 };
@@ -226,23 +232,32 @@ __device__ __forceinline__ void act_d2(int act, float z0, float& a0, float& s1, 
     }
 }
 
-// z-jet -> a-jet, in place
-template <int N1, int N2>
-__device__ __forceinline__ void act_forward(int act, float (&z)[1 + N1 + N2]) {
+// z-jet -> a-jet, in place.  WL > 0: the single second-order channel is the weighted combination L = sum_d w[d] D_d^2.
+template <int N1, int N2, int WL>
+__device__ __forceinline__ void act_forward(int act, float (&z)[1 + N1 + N2], const float* w) {
     float a0, s1, s2;
     act_d2(act, z[0], a0, s1, s2);
+    if constexpr (WL > 0) {
+        static_assert(N2 == 1, "combined mode carries one second-order channel");
+        float q = 0.0f;
 #pragma unroll
-    for (int s = 0; s < N2; ++s) z[1 + N1 + s] = fmaf(s2 * z[1 + s], z[1 + s], s1 * z[1 + N1 + s]);
+        for (int d = 0; d < WL; ++d) q = fmaf(w[d] * z[1 + d], z[1 + d], q);
+        z[1 + N1] = fmaf(s2, q, s1 * z[1 + N1]);
+    } else {
+#pragma unroll
+        for (int s = 0; s < N2; ++s) z[1 + N1 + s] = fmaf(s2 * z[1 + s], z[1 + s], s1 * z[1 + N1 + s]);
+    }
 #pragma unroll
     for (int f = 0; f < N1; ++f) z[1 + f] *= s1;
     z[0] = a0;
 }
 
-// reverse of the activation jet: given z-jet and the adjoint of the a-jet, produce a-jet (for the weight-gradient GEMM)
-// and the adjoint of the z-jet.
-template <int N1, int N2>
+// reverse of the activation jet: given the stored record (channel 0 = tanh(z0) for tanh nets, z0 for sin nets; other
+// channels z-jets) and the adjoint of the a-jet, produce the a-jet (for the weight-gradient GEMM) and the adjoint of the
+// z-jet.
+template <int N1, int N2, int WL>
 __device__ __forceinline__ void act_backward(int act, const float (&z)[1 + N1 + N2], const float (&ab)[1 + N1 + N2],
-                                             float (&a)[1 + N1 + N2], float (&zb)[1 + N1 + N2]) {
+                                             float (&a)[1 + N1 + N2], float (&zb)[1 + N1 + N2], const float* w) {
     float a0, s1, s2, s3;
     if (act == PJ_ACT_TANH) {   // record channel 0 = tanh(z0), stored by K1: no transcendental in the reverse pass
         a0 = z[0];
@@ -261,13 +276,27 @@ __device__ __forceinline__ void act_backward(int act, const float (&z)[1 + N1 + 
         zb0 = fmaf(s2 * z[1 + f], ab[1 + f], zb0);
         a[1 + f] = s1 * z[1 + f];
     }
+    if constexpr (WL > 0) {
+        const float abL = ab[1 + N1], zL = z[1 + N1];
+        float q = 0.0f;
 #pragma unroll
-    for (int s = 0; s < N2; ++s) {
-        const float zf = z[1 + s], zs = z[1 + N1 + s], abs_ = ab[1 + N1 + s];
-        zb[1 + N1 + s] = s1 * abs_;
-        zb[1 + s] = fmaf(2.0f * s2 * zf, abs_, zb[1 + s]);
-        zb0 = fmaf(fmaf(s3 * zf, zf, s2 * zs), abs_, zb0);
-        a[1 + N1 + s] = fmaf(s2 * zf, zf, s1 * zs);
+        for (int d = 0; d < WL; ++d) {
+            const float wz = w[d] * z[1 + d];
+            q = fmaf(wz, z[1 + d], q);
+            zb[1 + d] = fmaf(2.0f * s2 * wz, abL, zb[1 + d]);
+        }
+        zb[1 + N1] = s1 * abL;
+        zb0 = fmaf(fmaf(s3, q, s2 * zL), abL, zb0);
+        a[1 + N1] = fmaf(s2, q, s1 * zL);
+    } else {
+#pragma unroll
+        for (int s = 0; s < N2; ++s) {
+            const float zf = z[1 + s], zs = z[1 + N1 + s], abs_ = ab[1 + N1 + s];
+            zb[1 + N1 + s] = s1 * abs_;
+            zb[1 + s] = fmaf(2.0f * s2 * zf, abs_, zb[1 + s]);
+            zb0 = fmaf(fmaf(s3 * zf, zf, s2 * zs), abs_, zb0);
+            a[1 + N1 + s] = fmaf(s2 * zf, zf, s1 * zs);
+        }
     }
     zb[0] = zb0;
     a[0] = a0;

@@ -2,8 +2,12 @@
 // PJ_N1 = PJ_N2 = -1 builds the scheme-independent helpers (K2b reduce, loss finalize).
 #include "pinnjet_k2.cuh"
 
-#define PJ_CAT3(a, b, c) a##b##_##c
-#define PJ_NAME(prefix, n1, n2) PJ_CAT3(prefix, n1, n2)
+#ifndef PJ_WL
+#define PJ_WL 0
+#endif
+#define PJ_CAT4(a, b, c, d) a##b##_##c##_##d
+#define PJ_NAME4(prefix, n1, n2, wl) PJ_CAT4(prefix, n1, n2, wl)
+#define PJ_NAME(prefix, n1, n2) PJ_NAME4(prefix, n1, n2, PJ_WL)
 
 namespace pj {
 
@@ -71,16 +75,16 @@ static cudaError_t configure(K kern, int& configured) {
 cudaError_t PJ_NAME(launch_k1_, PJ_N1, PJ_N2)(const K1Args& a, int grid, int smem, cudaStream_t s) {
     static int c128 = 0, c256 = 0;
     if (a.plan.ntc1 == 128) {
-        auto kern = k1_forward_kernel<128, kMinB1_128, kP1, 4, PJ_N1, PJ_N2>;
+        auto kern = k1_forward_kernel<128, kMinB1_128, kP1, 4, PJ_N1, PJ_N2, PJ_WL>;
         if (cudaError_t e = configure(kern, c128)) return e;
         kern<<<grid, 160, smem, s>>>(a);
     } else if (a.plan.Q1 == 8) {
-        auto kern = k1_forward_kernel<256, 1, kP1, kQ1, PJ_N1, PJ_N2>;
+        auto kern = k1_forward_kernel<256, 1, kP1, kQ1, PJ_N1, PJ_N2, PJ_WL>;
         if (cudaError_t e = configure(kern, c256)) return e;
         kern<<<grid, 320, smem, s>>>(a);
     } else {
         static int c256q4 = 0;
-        auto kern = k1_forward_kernel<256, 1, kP1, 4, PJ_N1, PJ_N2>;
+        auto kern = k1_forward_kernel<256, 1, kP1, 4, PJ_N1, PJ_N2, PJ_WL>;
         if (cudaError_t e = configure(kern, c256q4)) return e;
         kern<<<grid, 320, smem, s>>>(a);
     }
@@ -90,11 +94,11 @@ cudaError_t PJ_NAME(launch_k1_, PJ_N1, PJ_N2)(const K1Args& a, int grid, int sme
 cudaError_t PJ_NAME(launch_k2_, PJ_N1, PJ_N2)(const K2Args& a, int grid, int smem, cudaStream_t s) {
     static int c128 = 0, c256 = 0;
     if (a.plan.ntc == 128) {
-        auto kern = k2_backward_kernel<128, kMinB2_128, kP, kQ, PJ_N1, PJ_N2>;
+        auto kern = k2_backward_kernel<128, kMinB2_128, kP, kQ, PJ_N1, PJ_N2, PJ_WL>;
         if (cudaError_t e = configure(kern, c128)) return e;
         kern<<<grid, 160, smem, s>>>(a);
     } else {
-        auto kern = k2_backward_kernel<256, 1, kP, kQ, PJ_N1, PJ_N2>;
+        auto kern = k2_backward_kernel<256, 1, kP, kQ, PJ_N1, PJ_N2, PJ_WL>;
         if (cudaError_t e = configure(kern, c256)) return e;
         kern<<<grid, 288, smem, s>>>(a);
     }
@@ -107,26 +111,26 @@ int PJ_NAME(occupancy_, PJ_N1, PJ_N2)(int which, int ntc, int smem) {
     cudaError_t e;
     static int c[4] = {0, 0, 0, 0};
     if (which == 1 && ntc == 128) {
-        auto kern = k1_forward_kernel<128, kMinB1_128, kP1, 4, PJ_N1, PJ_N2>;
+        auto kern = k1_forward_kernel<128, kMinB1_128, kP1, 4, PJ_N1, PJ_N2, PJ_WL>;
         configure(kern, c[0]);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 160, smem);
     } else if (which == 1 || which == 3) {   // 3: 256-thread K1 with the 4-unit tile (narrow nets without room for 2 CTAs)
         if (which == 1) {
-            auto kern = k1_forward_kernel<256, 1, kP1, kQ1, PJ_N1, PJ_N2>;
+            auto kern = k1_forward_kernel<256, 1, kP1, kQ1, PJ_N1, PJ_N2, PJ_WL>;
             configure(kern, c[1]);
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 320, smem);
         } else {
             static int cq4 = 0;
-            auto kern = k1_forward_kernel<256, 1, kP1, 4, PJ_N1, PJ_N2>;
+            auto kern = k1_forward_kernel<256, 1, kP1, 4, PJ_N1, PJ_N2, PJ_WL>;
             configure(kern, cq4);
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 320, smem);
         }
     } else if (ntc == 128) {
-        auto kern = k2_backward_kernel<128, kMinB2_128, kP, kQ, PJ_N1, PJ_N2>;
+        auto kern = k2_backward_kernel<128, kMinB2_128, kP, kQ, PJ_N1, PJ_N2, PJ_WL>;
         configure(kern, c[2]);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 160, smem);
     } else {
-        auto kern = k2_backward_kernel<256, 1, kP, kQ, PJ_N1, PJ_N2>;
+        auto kern = k2_backward_kernel<256, 1, kP, kQ, PJ_N1, PJ_N2, PJ_WL>;
         configure(kern, c[3]);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 288, smem);
     }

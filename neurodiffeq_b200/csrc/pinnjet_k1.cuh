@@ -70,9 +70,9 @@ struct RingCursor {
 
 // z-jets of P points of one unit (registers) -> workspace record (train), activation-jet rule, a-jets -> shared memory.
 // Record channel 0 holds tanh(z0) for tanh nets (the reverse pass then needs no transcendental) and z0 for sin nets.
-template <int P, int N1, int N2>
+template <int P, int N1, int N2, int WL>
 __device__ __forceinline__ void finish_unit(float (&zq)[P][1 + N1 + N2], int act_kind, float* __restrict__ act_row, int T,
-                                            float* __restrict__ rec_row, int T2) {
+                                            float* __restrict__ rec_row, int T2, const float (&wq)[P][WL > 0 ? WL : 1]) {
     constexpr int C = 1 + N1 + N2;
     auto store = [](float* dst, const float (&v)[P][C], int c) {
         if constexpr (P == 4)
@@ -88,7 +88,7 @@ __device__ __forceinline__ void finish_unit(float (&zq)[P][1 + N1 + N2], int act
         for (int c = 1; c < C; ++c) store(rec_row + c * T2, zq, c);
     }
 #pragma unroll
-    for (int p = 0; p < P; ++p) act_forward<N1, N2>(act_kind, zq[p]);
+    for (int p = 0; p < P; ++p) act_forward<N1, N2, WL>(act_kind, zq[p], wq[p]);
     if (rec_row) {
         if (act_kind == PJ_ACT_TANH) {
 #pragma unroll
@@ -103,7 +103,7 @@ __device__ __forceinline__ void finish_unit(float (&zq)[P][1 + N1 + N2], int act
     for (int c = 0; c < C; ++c) store(act_row + c * T, zq, c);
 }
 
-template <int NTC, int MINB, int P, int Q, int N1, int N2>
+template <int NTC, int MINB, int P, int Q, int N1, int N2, int WL>
 __global__ void __launch_bounds__(NTC + (NTC == 128 ? 32 : 64), MINB) k1_forward_kernel(const __grid_constant__ K1Args A) {
     constexpr int C = 1 + N1 + N2;
     // service warps after the compute warps: 128-thread CTAs (weights always resident: the producer only issues the initial
@@ -119,6 +119,9 @@ __global__ void __launch_bounds__(NTC + (NTC == 128 ? 32 : 64), MINB) k1_forward
     float* ycache = reinterpret_cast<float*>(smem + pl.k1_ycache);
     float* slots = reinterpret_cast<float*>(smem + pl.k1_slots);
     int4* prog_s = reinterpret_cast<int4*>(smem + pl.k1_prog);
+    int4* progw_s = reinterpret_cast<int4*>(smem + pl.k1_progw);      // weight program (WL > 0)
+    float* wbuf = reinterpret_cast<float*>(smem + pl.k1_wbuf);       // [n_nets*WL][T] weights of this tile's points
+    float* wslots = reinterpret_cast<float*>(smem + pl.k1_wslots);   // value file of the weight program (compute threads)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + pl.k1_misc);
     uint64_t* empty = full + MAX_STAGES;
     uint64_t* yfull = empty + MAX_STAGES;    // [2] jet table of a batch complete -> program warp
@@ -144,6 +147,8 @@ __global__ void __launch_bounds__(NTC + (NTC == 128 ? 32 : 64), MINB) k1_forward
     }
     for (int i = tid; i < pl.small_floats; i += NT_TOTAL) small[i] = __ldg(A.pack + i);
     for (int i = tid; i < A.prog_len; i += NT_TOTAL) prog_s[i] = __ldg(A.prog + i);
+    if constexpr (WL > 0)
+        for (int i = tid; i < A.prog_w_len; i += NT_TOTAL) progw_s[i] = __ldg(A.prog_w + i);
     __syncthreads();
 
     if (warp == N_CWARPS) {   // ---------------- producer warp ----------------
@@ -207,11 +212,32 @@ __global__ void __launch_bounds__(NTC + (NTC == 128 ? 32 : 64), MINB) k1_forward
         }
         const bool rec = train && (base + p0 < ws_points);
         float* zj_tile = rec ? A.zj + ((base + p0) / T2) * pl.zj_tile_floats + (p0 % T2) : nullptr;
+        if constexpr (WL > 0) {   // per-point weights of the combined second-order channel (coordinate-only expressions)
+            const int NW = sp.n_nets * WL;
+            if (tid < T) {
+                ProgIO io{A.coords, min(base + tid, A.N - 1), A.N, nullptr, 0, nullptr, 0.0f, nullptr, nullptr, nullptr, T2};
+                io.w_out = wbuf + tid;
+                io.w_stride = T;
+                run_program<NTC>(progw_s, A.prog_w_len, wslots + tid, io);
+            }
+            bar_compute<NTC>();
+            if (train)   // K2 needs the same weights: workspace [tile2][NW][T2]
+                for (int e = tid; e < NW * T; e += NT_COMPUTE) {
+                    const int row = e / T, pt = e - row * T;
+                    const long long gp = base + pt;
+                    if (gp < ws_points) A.wts[(gp / T2) * ((long long)NW * T2) + row * T2 + (gp % T2)] = wbuf[e];
+                }
+        }
 
         for (int n = 0; n < sp.n_nets; ++n) {
             const PjNet& net = sp.net[n];
             const int L = net.n_linear - 1;   // hidden layers
             const int act_kind = net.act;
+            float wq[P][WL > 0 ? WL : 1];
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+#pragma unroll
+                for (int dd = 0; dd < (WL > 0 ? WL : 1); ++dd) wq[p][dd] = WL > 0 ? wbuf[(n * WL + dd) * T + p0 + p] : 0.0f;
 
             // ---------------- Linear 0: coordinates -> hidden 1 (first-order channels are columns of W) ----------------
             {
@@ -253,7 +279,7 @@ __global__ void __launch_bounds__(NTC + (NTC == 128 ? 32 : 64), MINB) k1_forward
 #pragma unroll
                             for (int s2 = 0; s2 < N2; ++s2) zq[p][1 + N1 + s2] = 0.0f;
                         }
-                        finish_unit<P, N1, N2>(zq, act_kind, act + u * RS + p0, T, rec ? zrow + u * RS2 : nullptr, T2);
+                        finish_unit<P, N1, N2, WL>(zq, act_kind, act + u * RS + p0, T, rec ? zrow + u * RS2 : nullptr, T2, wq);
                     }
                 }
             }
@@ -292,7 +318,7 @@ __global__ void __launch_bounds__(NTC + (NTC == 128 ? 32 : 64), MINB) k1_forward
                         for (int c = 0; c < C; ++c)
 #pragma unroll
                             for (int p = 0; p < P; ++p) zq[p][c] = pick<P>(acc[q][c], p) + (c == 0 ? bias : 0.0f);
-                        finish_unit<P, N1, N2>(zq, act_kind, act + u * RS + p0, T, rec ? zrow + u * RS2 : nullptr, T2);
+                        finish_unit<P, N1, N2, WL>(zq, act_kind, act + u * RS + p0, T, rec ? zrow + u * RS2 : nullptr, T2, wq);
                     }
                 }
                 bar_compute<NTC>();

@@ -40,7 +40,7 @@ __device__ __forceinline__ void wgrad_tile(f2 (&acc)[WJ][WK], const float* __res
     }
 }
 
-template <int NTC, int MINB, int P, int Q, int N1, int N2>
+template <int NTC, int MINB, int P, int Q, int N1, int N2, int WL>
 __global__ void __launch_bounds__(NTC + 32, MINB) k2_backward_kernel(const __grid_constant__ K2Args A) {
     constexpr int C = 1 + N1 + N2;
     constexpr int NT_COMPUTE = NTC, NT_TOTAL = NTC + 32, N_CWARPS = NTC / 32;
@@ -105,6 +105,12 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k2_backward_kernel(const __gri
             const int act_kind = net.act;
             const int n_out = net.width[net.n_linear];
             const int hpL = pl.hp[n][L];
+            float wq[P][WL > 0 ? WL : 1];   // weights of the combined second-order channel at this thread's points
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+#pragma unroll
+                for (int dd = 0; dd < (WL > 0 ? WL : 1); ++dd)
+                    wq[p][dd] = WL > 0 ? __ldg(A.wts + tile * ((long long)sp.n_nets * WL * T) + (n * WL + dd) * T + p0 + p) : 0.0f;
 
             // (0) seeds of this net + bulk load of the last hidden layer's z-jets
             if (tid == 0) {
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k2_backward_kernel(const __gri
 #pragma unroll
                                     for (int c = 0; c < C; ++c) ab[c] = fmaf(w, ybar[(o * C + c) * T + pt], ab[c]);
                                 }
-                            act_backward<N1, N2>(act_kind, z, ab, a, zb);
+                            act_backward<N1, N2, WL>(act_kind, z, ab, a, zb, wq[p]);
 #pragma unroll
                             for (int o = 0; o < PJ_MAX_NETS; ++o)
                                 if (o < n_out) {
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k2_backward_kernel(const __gri
                                 z[c] = Zb[u * RS + c * T + p0 + p];
                                 ab[c] = pick<P>(acc[q][c], p);
                             }
-                            act_backward<N1, N2>(act_kind, z, ab, av[p], zv[p]);
+                            act_backward<N1, N2, WL>(act_kind, z, ab, av[p], zv[p], wq[p]);
                             gb += zv[p][0];
                         }
 #pragma unroll

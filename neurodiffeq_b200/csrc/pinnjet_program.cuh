@@ -21,6 +21,8 @@ struct ProgIO {
     float* r_out;                 // [n_eq][N] or nullptr
     float* seed_tile;             // seeds of this point's tile: row * T + pt, or nullptr
     int T;
+    float* w_out = nullptr;       // weight program: OP_ST_W row -> w_out[row * w_stride]
+    int w_stride = 0;
 };
 
 // returns sum of squared residuals of this point
@@ -44,6 +46,9 @@ __device__ __forceinline__ float run_program(const int4* __restrict__ prog, int 
                 case OP_RBAR: v = __ldg(io.rbar + (long long)ins.z * io.N + io.gidx); break;
                 default: v = io.loss_scale; break;
             }
+        } else if (op == OP_ST_W) {
+            io.w_out[ins.y * io.w_stride] = slot[ins.z * SLOT_STRIDE];
+            continue;
         } else if (op >= OP_ST_U && op <= OP_ST_SEED) {
             const float a = slot[ins.z * SLOT_STRIDE];
             if (op == OP_ST_U) {

@@ -18,6 +18,12 @@ _LIB_PATH = os.environ.get("PINNJET_LIB", os.path.join(_HERE, "csrc", "libpinnje
 
 PJ_MAX_NETS, PJ_MAX_LINEAR, PJ_MAX_COORDS, PJ_MAX_DIRS = 4, 8, 8, 4
 SUPPORTED_SCHEMES = [(1, 0), (1, 1), (2, 0), (2, 1), (2, 2), (3, 0), (3, 3)]
+COMBINED_SCHEMES = [(2, 2), (3, 3)]   # (n1, n2) that also exist with ONE weighted second-order channel (wl = n2)
+
+
+def combine_seconds(n1, n2):
+    """May the n2 pure second-order channels be replaced by one weighted combination?  (PINNJET_NO_COMBINE=1: never.)"""
+    return os.environ.get("PINNJET_NO_COMBINE") != "1" and (n1, n2) in COMBINED_SCHEMES
 
 
 class PjNet(ctypes.Structure):
@@ -28,7 +34,7 @@ class PjNet(ctypes.Structure):
 
 class PjSpec(ctypes.Structure):
     _fields_ = [("abi_version", ctypes.c_int32), ("n_coords", ctypes.c_int32), ("n_nets", ctypes.c_int32),
-                ("n1", ctypes.c_int32), ("n2", ctypes.c_int32),
+                ("n1", ctypes.c_int32), ("n2", ctypes.c_int32), ("wl", ctypes.c_int32),
                 ("dir", (ctypes.c_float * PJ_MAX_COORDS) * PJ_MAX_DIRS),
                 ("n_funcs", ctypes.c_int32), ("n_eq", ctypes.c_int32), ("n_yrows", ctypes.c_int32),
                 ("n_slots", ctypes.c_int32), ("n_theta", ctypes.c_int64), ("net", PjNet * PJ_MAX_NETS)]
@@ -63,14 +69,14 @@ def load_library():
     lib.pj_plan_info.argtypes = [ctypes.POINTER(PjSpec), i64, ctypes.POINTER(i64), i32]
     lib.pj_plan_info.restype = ctypes.c_int
     lib.pj_pack.argtypes = [ctypes.POINTER(PjSpec), vp, vp, vp]
-    lib.pj_forward.argtypes = [ctypes.POINTER(PjSpec), vp, i32, ctypes.POINTER(vp), i64, vp, vp, vp, vp, vp,
+    lib.pj_forward.argtypes = [ctypes.POINTER(PjSpec), vp, i32, vp, i32, ctypes.POINTER(vp), i64, vp, vp, vp, vp, vp,
                                ctypes.c_size_t, vp]
-    lib.pj_forward_train.argtypes = [ctypes.POINTER(PjSpec), vp, i32, ctypes.POINTER(vp), i64, vp, f32, vp, vp, vp, vp,
-                                     ctypes.c_size_t, vp]
+    lib.pj_forward_train.argtypes = [ctypes.POINTER(PjSpec), vp, i32, vp, i32, ctypes.POINTER(vp), i64, vp, f32, vp, vp,
+                                     vp, vp, ctypes.c_size_t, vp]
     lib.pj_backward.argtypes = [ctypes.POINTER(PjSpec), ctypes.POINTER(vp), i64, vp, vp, vp, ctypes.c_size_t, vp]
     for fn in (lib.pj_sizes, lib.pj_pack, lib.pj_forward, lib.pj_forward_train, lib.pj_backward):
         fn.restype = ctypes.c_int
-    if lib.pj_abi_version() != 1:
+    if lib.pj_abi_version() != 2:
         raise RuntimeError("libpinnjet.so ABI version mismatch")
     _lib = lib
     return lib
@@ -107,7 +113,8 @@ class FusedProblem:
                 raise RuntimeError("the fused PINN engine needs a CUDA device (B200, sm_100a); none is visible")
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
-        self.tp = TracedProblem(nets, conditions, diff_eqs, n_coords, coords_for_condition, pad_scheme=pad_scheme)
+        self.tp = TracedProblem(nets, conditions, diff_eqs, n_coords, coords_for_condition, pad_scheme=pad_scheme,
+                                combine_seconds=combine_seconds)
         tp = self.tp
         self.n_coords, self.n_funcs, self.n_eq = n_coords, tp.n_funcs, tp.n_eq
         self._adopt_parameters()
@@ -115,6 +122,7 @@ class FusedProblem:
         dev = self.device
         self.prog_eval = torch.from_numpy(tp.prog_eval.code.copy()).to(dev)
         self.prog_train = torch.from_numpy(tp.prog_train.code.copy()).to(dev)
+        self.prog_w = torch.from_numpy(tp.prog_w.code.copy()).to(dev) if tp.wl else None
         self._prog_train_ext = None
         self._sizes_cache = {}
         self.pack_buf = None
@@ -174,18 +182,20 @@ class FusedProblem:
     def _build_spec(self):
         tp = self.tp
         sp = PjSpec()
-        sp.abi_version = 1
+        sp.abi_version = 2
         sp.n_coords = tp.n_coords
         sp.n_nets = len(tp.nets)
         if sp.n_nets > PJ_MAX_NETS:
             raise NotImplementedError(f"{sp.n_nets} distinct networks (max {PJ_MAX_NETS})")
-        sp.n1, sp.n2 = tp.scheme.n1, tp.scheme.n2
+        sp.n1, sp.n2 = tp.scheme.n1, (1 if tp.wl else tp.scheme.n2)
+        sp.wl = tp.wl
         dirs = tp.direction_matrix()
         for f in range(tp.scheme.n1):
             for i in range(tp.n_coords):
                 sp.dir[f][i] = float(dirs[f, i])
         sp.n_funcs, sp.n_eq, sp.n_yrows = tp.n_funcs, tp.n_eq, tp.n_yrows
-        sp.n_slots = max(tp.prog_eval.n_slots, tp.prog_train.n_slots, tp.prog_train_ext.n_slots)
+        sp.n_slots = max(tp.prog_eval.n_slots, tp.prog_train.n_slots, tp.prog_train_ext.n_slots,
+                         tp.prog_w.n_slots if tp.wl else 1)
         sp.n_theta = self.n_theta
         k = 0
         for n, nd in enumerate(tp.nets):
@@ -249,6 +259,9 @@ class FusedProblem:
             arr[i] = c.data_ptr()
         return arr, keep
 
+    def _prog_w_args(self):
+        return (self.prog_w.data_ptr(), len(self.tp.prog_w)) if self.tp.wl else (None, 0)
+
     # ---- kernels ------------------------------------------------------------------------------------------------------
     def pack(self):
         """K0: re-layout theta for the kernels.  Must run after every change of the parameters (optimizer step)."""
@@ -269,7 +282,8 @@ class FusedProblem:
         r = torch.empty((self.n_eq, n), dtype=torch.float32, device=self.device) if want_residual else None
         if want_sumsq:
             self.sumsq.zero_()
-        _check(self.lib.pj_forward(ctypes.byref(self.spec), self.prog_eval.data_ptr(), len(self.tp.prog_eval), ptrs, n,
+        _check(self.lib.pj_forward(ctypes.byref(self.spec), self.prog_eval.data_ptr(), len(self.tp.prog_eval),
+                                   *self._prog_w_args(), ptrs, n,
                                    self.pack_buf.data_ptr(), u.data_ptr() if want_u else None,
                                    r.data_ptr() if want_residual else None,
                                    self.sumsq.data_ptr() if want_sumsq else None,
@@ -297,7 +311,7 @@ class FusedProblem:
             rbar = rbar.detach().to(self.device, torch.float32).contiguous()
             if tuple(rbar.shape) != (self.n_eq, n):
                 raise ValueError(f"rbar must have shape ({self.n_eq}, {n})")
-        _check(self.lib.pj_forward_train(ctypes.byref(self.spec), prog.data_ptr(), prog_len, ptrs, n,
+        _check(self.lib.pj_forward_train(ctypes.byref(self.spec), prog.data_ptr(), prog_len, *self._prog_w_args(), ptrs, n,
                                          self.pack_buf.data_ptr(), ctypes.c_float(scale),
                                          rbar.data_ptr() if rbar is not None else None,
                                          r.data_ptr() if want_residual else None, sumsq_out.data_ptr(),

@@ -29,6 +29,7 @@ OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG = 5, 6, 7, 8, 9
 OP_SIN, OP_COS, OP_EXP, OP_LOG, OP_TANH, OP_SQRT, OP_ABS, OP_SIGN, OP_POWC, OP_RCP = 10, 11, 12, 13, 14, 15, 16, 17, 18, 19
 OP_ST_U, OP_ST_R, OP_ST_SEED = 20, 21, 22
 OP_TAN, OP_SINH, OP_COSH, OP_ATAN, OP_ERF = 23, 24, 25, 26, 27
+OP_ST_W = 28   # store a per-point weight of the combined second-order channel
 
 _UNARY = {"neg": OP_NEG, "sin": OP_SIN, "cos": OP_COS, "exp": OP_EXP, "log": OP_LOG, "tanh": OP_TANH,
           "sqrt": OP_SQRT, "abs": OP_ABS, "sign": OP_SIGN, "rcp": OP_RCP, "tan": OP_TAN, "sinh": OP_SINH,
@@ -835,11 +836,17 @@ def lower(outputs, yrow_of):
     return Program(code, max(n_slots, 1), exact)
 
 
-def evaluate_program(program, coords, y, rbar=None, params=None, n_u=0, n_r=0, n_seed=0):
+def depends_on_jets(expr):
+    """True if the expression reads any network-output jet (i.e. is not a function of the coordinates alone)."""
+    return any(n.op in ("net", "ych") for n in topo_order([expr]))
+
+
+def evaluate_program(program, coords, y, rbar=None, params=None, n_u=0, n_r=0, n_seed=0, n_w=0):
     """Pure-numpy interpreter of the bytecode (host-side check of the lowering; float64)."""
     n = coords.shape[1]
     val = np.zeros((program.n_slots, n))
     u, r, seed = np.zeros((n_u, n)), np.zeros((n_r, n)), np.zeros((n_seed, n))
+    wout = np.zeros((n_w, n))
     bits = lambda b: float(np.array([b], dtype=np.int32).view(np.float32)[0])  # noqa: E731
     un = {OP_NEG: np.negative, OP_SIN: np.sin, OP_COS: np.cos, OP_EXP: np.exp, OP_LOG: np.log, OP_TANH: np.tanh,
           OP_SQRT: np.sqrt, OP_ABS: np.abs, OP_SIGN: np.sign, OP_RCP: lambda a: 1.0 / a, OP_TAN: np.tan,
@@ -874,6 +881,10 @@ def evaluate_program(program, coords, y, rbar=None, params=None, n_u=0, n_r=0, n
             r[dst] = val[a]
         elif op == OP_ST_SEED:
             seed[dst] = val[a]
+        elif op == OP_ST_W:
+            wout[dst] = val[a]
         else:
             val[dst] = un[op](val[a])
+    if n_w:
+        return wout
     return u, r, seed

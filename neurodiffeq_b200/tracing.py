@@ -74,7 +74,8 @@ class NetDescription:
 
 
 class TracedProblem:
-    def __init__(self, nets, conditions, diff_eqs, n_coords, coords_for_condition=None, pad_scheme=None):
+    def __init__(self, nets, conditions, diff_eqs, n_coords, coords_for_condition=None, pad_scheme=None,
+                 combine_seconds=None):
         """``nets[k]`` / ``conditions[k]`` as in the reference solver; ``diff_eqs(*funcs, *coords)``.
         ``coords_for_condition(k, cond, coords) -> tuple`` lets SolverSpherical trim coordinates
         (reference solvers.py:894-916)."""
@@ -129,13 +130,70 @@ class TracedProblem:
         resolved = S.substitute(funcs + residuals, mapping)
         self.funcs, self.residuals = resolved[:self.n_funcs], resolved[self.n_funcs:]
 
+        # --- combined second-order channel ("forward Laplacian" with per-point weights) ---------------------------------
+        # If a residual is AFFINE in the pure second derivatives of a network output with coefficients that depend on the
+        # coordinates only (Laplacians, spherical/cylindrical Laplacians, diffusion terms, ...), the kernels can carry ONE
+        # channel  L = sum_d w_d(x) D_d^2  instead of n2 separate ones: linear layers commute with the weighted sum and the
+        # activation rule becomes  a_L = s'' * sum_d w_d z_d^2 + s' z_L.  C drops from 1+n1+n2 to 2+n1 (C2: 5 -> 4 channels,
+        # C4: 7 -> 5); the executed FLOPs shrink accordingly, the result is the same function of theta.
+        self.wl = 0
+        self.weight_exprs = []
+        if combine_seconds is not None and combine_seconds(self.scheme.n1, self.scheme.n2):
+            self._try_combine_seconds()
+            C = self.n_channels
+            self.yrow0, row = [], 0
+            for nd in self.nets:
+                self.yrow0.append(row)
+                row += nd.n_out * C
+            self.n_yrows = row
+
         yrow = lambda net_idx, o, c: self.yrow0[net_idx] + o * C + c  # noqa: E731
         self._yrow = yrow
+        self.prog_w = S.lower([(S.OP_ST_W, row, e) for row, e in self.weight_exprs], yrow) if self.wl else None
         # --- programs ---------------------------------------------------------------------------------------------------
         self.prog_eval = S.lower([(S.OP_ST_U, k, f) for k, f in enumerate(self.funcs)]
                                  + [(S.OP_ST_R, e, r) for e, r in enumerate(self.residuals)], yrow)
         self.prog_train = self._train_program(external_rbar=False)
         self._prog_train_ext = None
+
+    @property
+    def n_channels(self):
+        return 2 + self.scheme.n1 if self.wl else self.scheme.n_channels
+
+    def _try_combine_seconds(self):
+        g = self.graph
+        n1, n2 = self.scheme.n1, self.scheme.n2
+        first_sec = 1 + n1
+        is_sec = lambda leaf: leaf.op == "ych" and leaf.imm[2] >= first_sec  # noqa: E731
+        for f in self.funcs:
+            if any(is_sec(n) for n in S.topo_order([f])):
+                return
+        zero = g.const(0.0)
+        owner, weights = {}, {}
+        for e, r in enumerate(self.residuals):
+            for leaf, coef in S.reverse_gradients([(r, g.const(1.0))]).items():
+                if not is_sec(leaf):
+                    continue
+                if S.depends_on_jets(coef):
+                    return                       # not affine in the second derivatives / jet-dependent coefficient
+                net_idx, o, c = leaf.imm
+                if owner.setdefault(net_idx, (e, o)) != (e, o):
+                    return                       # two equations / outputs need different combinations of one net's jets
+                weights.setdefault(net_idx, [zero] * n2)[c - first_sec] = coef
+        if not owner:
+            return
+        new_res = list(self.residuals)
+        for net_idx, (e, o) in owner.items():
+            zero_map = {}
+            for node in S.topo_order([new_res[e]]):
+                if is_sec(node) and node.imm[0] == net_idx:
+                    zero_map[node] = zero
+            rest = S.substitute([new_res[e]], zero_map)[0]
+            new_res[e] = g.add(rest, g.ych(net_idx, o, first_sec))
+        self.residuals = new_res
+        self.wl = n2
+        self.weight_exprs = [(n * n2 + d, weights.get(n, [zero] * n2)[d]) for n in range(len(self.nets))
+                             for d in range(n2)]
 
     def _train_program(self, external_rbar):
         g = self.graph

@@ -24,11 +24,13 @@ def act_derivs(act, z0):
     return a, s1, -a, -s1
 
 
-def forward_jets(weights, biases, act, x_in, dirs_in, n2):
+def forward_jets(weights, biases, act, x_in, dirs_in, n2, wl=None):
     """weights[l]: [out,in] (torch layout); x_in: [n_in, N]; dirs_in: [n1, n_in] direction vectors restricted to the
     network inputs.  Channels: 0 value | 1..n1 first order | n1+1..n1+n2 pure second order of the first n2 dirs.
     Returns (z_jets per hidden layer [C, h, N], y [C, n_out, N])."""
     n1 = dirs_in.shape[0]
+    if wl is not None:   # combined second-order channel L = sum_d wl[d] * D_d^2  (wl: [n_dirs_weighted, N])
+        n2 = 1
     C = 1 + n1 + n2
     N = x_in.shape[1]
     a = np.zeros((C, x_in.shape[0], N))
@@ -44,36 +46,35 @@ def forward_jets(weights, biases, act, x_in, dirs_in, n2):
         if l == L - 1:
             return z_store, z
         z_store.append(z)
-        a0, s1, s2, _ = act_derivs(act, z[0])
-        a = np.empty_like(z)
-        a[0] = a0
-        for f in range(n1):
-            a[1 + f] = s1 * z[1 + f]
-        for s in range(n2):
-            a[1 + n1 + s] = s2 * z[1 + s] ** 2 + s1 * z[1 + n1 + s]
+        a = a_from_z(act, z, n1, n2, wl)
 
 
-def a_from_z(act, z, n1, n2):
+def a_from_z(act, z, n1, n2, wl=None):
     a0, s1, s2, _ = act_derivs(act, z[0])
     a = np.empty_like(z)
     a[0] = a0
     for f in range(n1):
         a[1 + f] = s1 * z[1 + f]
+    if wl is not None:
+        a[1 + n1] = s2 * sum(wl[d] * z[1 + d] ** 2 for d in range(wl.shape[0])) + s1 * z[1 + n1]
+        return a
     for s in range(n2):
         a[1 + n1 + s] = s2 * z[1 + s] ** 2 + s1 * z[1 + n1 + s]
     return a
 
 
-def backward(weights, act, x_in, dirs_in, n2, z_store, ybar):
+def backward(weights, act, x_in, dirs_in, n2, z_store, ybar, wl=None):
     """ybar: [C, n_out, N] seeds dL/dy.  Returns (grad_W list [out,in], grad_b list)."""
     n1 = dirs_in.shape[0]
+    if wl is not None:
+        n2 = 1
     C = 1 + n1 + n2
     L = len(weights)
     gW, gb = [None] * L, [None] * L
     zbar = ybar
     for l in range(L - 1, -1, -1):
         if l > 0:
-            a_prev = a_from_z(act, z_store[l - 1], n1, n2)
+            a_prev = a_from_z(act, z_store[l - 1], n1, n2, wl)
         else:
             a_prev = np.zeros((C, x_in.shape[0], x_in.shape[1]))
             a_prev[0] = x_in
@@ -91,10 +92,19 @@ def backward(weights, act, x_in, dirs_in, n2, z_store, ybar):
         for f in range(n1):
             zb[1 + f] = s1 * abar[1 + f]
             zb[0] += s2 * z[1 + f] * abar[1 + f]
-        for s in range(n2):
-            zb[1 + n1 + s] = s1 * abar[1 + n1 + s]
-            zb[1 + s] += 2.0 * s2 * z[1 + s] * abar[1 + n1 + s]
-            zb[0] += (s3 * z[1 + s] ** 2 + s2 * z[1 + n1 + s]) * abar[1 + n1 + s]
+        if wl is not None:
+            aL = abar[1 + n1]
+            zb[1 + n1] = s1 * aL
+            q = 0.0
+            for d in range(wl.shape[0]):
+                zb[1 + d] += 2.0 * s2 * wl[d] * z[1 + d] * aL
+                q = q + wl[d] * z[1 + d] ** 2
+            zb[0] += (s3 * q + s2 * z[1 + n1]) * aL
+        else:
+            for s in range(n2):
+                zb[1 + n1 + s] = s1 * abar[1 + n1 + s]
+                zb[1 + s] += 2.0 * s2 * z[1 + s] * abar[1 + n1 + s]
+                zb[0] += (s3 * z[1 + s] ** 2 + s2 * z[1 + n1 + s]) * abar[1 + n1 + s]
         zbar = zb
     return gW, gb
 
@@ -109,16 +119,20 @@ def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True):
     N = coords.shape[1]
     dirs = np.asarray(tp.scheme.dirs, dtype=np.float64).reshape(tp.scheme.n1, tp.n_coords)
     n1, n2 = tp.scheme.n1, tp.scheme.n2
-    C = 1 + n1 + n2
+    C = tp.n_channels
+    wl_all = None
+    if getattr(tp, "wl", 0):
+        wl_all = S.evaluate_program(tp.prog_w, coords, np.zeros((1, N)), n_w=len(tp.nets) * tp.wl)
     y_rows = np.zeros((tp.n_yrows, N))
     stores = []
     for k, nd in enumerate(tp.nets):
+        wl = wl_all[k * tp.wl:(k + 1) * tp.wl] if wl_all is not None else None
         Ws = [np.asarray(p, dtype=np.float64) for p in params_per_net[k][0::2]]
         bs = [np.asarray(p, dtype=np.float64) for p in params_per_net[k][1::2]]
         x_in = coords[list(nd.in_coord)]
         d_in = dirs[:, list(nd.in_coord)]
-        z_store, y = forward_jets(Ws, bs, nd.act, x_in, d_in, n2)
-        stores.append((Ws, x_in, d_in, z_store))
+        z_store, y = forward_jets(Ws, bs, nd.act, x_in, d_in, n2, wl)
+        stores.append((Ws, x_in, d_in, z_store, wl))
         for o in range(nd.n_out):
             for c in range(C):
                 y_rows[tp.yrow0[k] + o * C + c] = y[c, o]
@@ -132,12 +146,12 @@ def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True):
         assert np.allclose(r2, r)
         grads = []
         for k, nd in enumerate(tp.nets):
-            Ws, x_in, d_in, z_store = stores[k]
+            Ws, x_in, d_in, z_store, wl = stores[k]
             ybar = np.zeros((C, nd.n_out, N))
             for o in range(nd.n_out):
                 for c in range(C):
                     ybar[c, o] = seeds[tp.yrow0[k] + o * C + c]
-            gW, gb = backward(Ws, nd.act, x_in, d_in, n2, z_store, ybar)
+            gW, gb = backward(Ws, nd.act, x_in, d_in, n2, z_store, ybar, wl)
             for w, b in zip(gW, gb):
                 grads += [w, b]
         out.update(grads=grads, seeds=seeds, z_store=[s[3] for s in stores])

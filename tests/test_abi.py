@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} not exported"
     from neurodiffeq_b200 import engine
     assert set(engine.EXPORTED_SYMBOLS) == declared
-    assert lib.pj_abi_version() == 1
+    assert lib.pj_abi_version() == 2
 
 
 def test_ctypes_struct_layout_matches_c(tmp_path):

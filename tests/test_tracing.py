@@ -55,6 +55,50 @@ def test_traced_problem_matches_reference_golden(key):
           "slots", tp.prog_train.n_slots)
 
 
+@pytest.mark.parametrize("key,wl,channels", [("c2", 2, 4), ("c4", 3, 5), ("c3", 0, 4), ("c5", 0, 2)])
+def test_combined_second_order_channel(key, wl, channels):
+    """Residuals affine in the pure second derivatives with coordinate-only coefficients are carried as ONE weighted
+    channel (forward-Laplacian style): C2 5 -> 4 channels, C4 7 -> 5; values and gradients are unchanged."""
+    from neurodiffeq_b200.tracing import TracedProblem
+    from neurodiffeq_b200.engine import pad_scheme
+    wl_, nets, conds, _ = trace(key)
+    tp = TracedProblem(nets, conds, workloads.bundle_eq_wrapper(wl_), len(wl_.coord_names), pad_scheme=pad_scheme,
+                       combine_seconds=lambda a, b: (a, b) in ((2, 2), (3, 3)))
+    assert tp.wl == wl and tp.n_channels == channels
+    gold = load_golden(wl_.name)
+    per_net, it = [], iter(gold["params"])
+    for nd in tp.nets:
+        per_net.append([next(it) for _ in range(2 * len(nd.linears))])
+    out = jet_numpy.run_traced(tp, per_net, gold["coords"])
+    rms = np.sqrt((gold["residual"] ** 2).mean())
+    assert np.abs(out["residual"] - gold["residual"]).max() <= 1e-9 * rms
+    gn = np.sqrt(sum((g ** 2).sum() for g in gold["grads"]))
+    dn = np.sqrt(sum(((g - h.reshape(g.shape)) ** 2).sum() for g, h in zip(gold["grads"], out["grads"])))
+    assert dn <= 1e-9 * gn
+
+
+def test_combined_channel_is_refused_when_not_affine():
+    from neurodiffeq_b200 import diff
+    from neurodiffeq_b200.networks import FCNN
+    from neurodiffeq_b200.conditions import NoCondition
+    from neurodiffeq_b200.tracing import TracedProblem
+    net = FCNN(2, 1, hidden_units=(8,))
+    always = lambda a, b: True  # noqa: E731
+    # u * u_xx: the coefficient of the second derivative depends on the network -> separate channels stay
+    tp = TracedProblem([net], [NoCondition()], lambda u, x, y: [u * diff(u, x, order=2) + diff(u, y, order=2)], 2,
+                       combine_seconds=always)
+    assert tp.wl == 0
+    # sin(u_xx): not affine
+    tp = TracedProblem([net], [NoCondition()], lambda u, x, y: [torch.sin(diff(u, x, order=2)) + diff(u, y, order=2)], 2,
+                       combine_seconds=always)
+    assert tp.wl == 0
+    # two equations that need different combinations of the same net's second derivatives
+    tp = TracedProblem([net], [NoCondition()],
+                       lambda u, x, y: [diff(u, x, order=2) + diff(u, y, order=2), diff(u, x, order=2) - diff(u, y, order=2)],
+                       2, combine_seconds=always)
+    assert tp.wl == 0
+
+
 def test_mixed_partials_by_polarisation():
     """u_xy is carried as (D_{x+y}^2 - D_x^2 - D_y^2)/2; checked against autograd on a random FCNN."""
     from neurodiffeq_b200 import diff
