@@ -178,6 +178,15 @@ class ClockSampler:
                 "power_w_max": max(self.power) if self.power else None, "samples": len(self.samples)}
 
 
+def executed_flops(wl, tp):
+    """F = sum over nets of 2*d0*h1 + C*2*(sum h_{l-1} h_l + h_L*d_out) with the channel count the kernels really carry."""
+    c_exec, total = tp.n_channels, 0
+    for widths, _ in wl.nets_spec:
+        d0, h = widths[0], widths[1:]
+        total += 2 * d0 * h[0] + c_exec * 2 * sum(a * b for a, b in zip(h[:-1], h[1:]))
+    return total
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -375,7 +384,7 @@ def main():
         # tracer proves the residual affine in the pure second derivatives, the kernels carry ONE weighted second-order
         # channel instead (forward-Laplacian): fewer channels are executed for the same result.
         "channels_canonical": 1 + fp.tp.scheme.n1 + fp.tp.scheme.n2, "channels_executed": fp.tp.n_channels,
-        "executed_flops_per_point": int(round(wl.flops_fwdjet * fp.tp.n_channels / (1 + fp.tp.scheme.n1 + fp.tp.scheme.n2))),
+        "executed_flops_per_point": executed_flops(wl, fp.tp),
         "k2": {"kernel": "k2_backward_kernel + k2_reduce_kernel", "algorithmic_flops_per_point": 2 * wl.flops_fwdjet,
                "launch_ms": k2_ms, "achieved": 2 * flops_k1 / (k2_ms * 1e-3) / 1e12,
                "frac_of_fp32_ffma_peak": 2 * flops_k1 / (k2_ms * 1e-3) / 1e12 / fp32_peak},
