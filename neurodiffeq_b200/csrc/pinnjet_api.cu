@@ -3,6 +3,9 @@
 #include <cstring>
 #include <cstdarg>
 
+#include <cstdlib>
+#include <cuda_bf16.h>
+
 #include "pinnjet_common.cuh"
 
 namespace pj {
@@ -11,6 +14,7 @@ namespace pj {
 #define PJ_DECL(N1, N2, WL)                                                                        \
     cudaError_t launch_k1_##N1##_##N2##_##WL(const K1Args& a, int grid, int smem, cudaStream_t s); \
     cudaError_t launch_k2_##N1##_##N2##_##WL(const K2Args& a, int grid, int smem, cudaStream_t s); \
+    cudaError_t launch_k1tc_##N1##_##N2##_##WL(const K1Args& a, int grid, int smem, cudaStream_t s); \
     int occupancy_##N1##_##N2##_##WL(int which, int ntc, int smem);
 PJ_DECL(1, 0, 0)
 PJ_DECL(1, 1, 0)
@@ -32,12 +36,13 @@ struct SchemeEntry {
     K1Launch k1;
     K2Launch k2;
     int (*occ)(int, int, int);
+    K1Launch k1tc;
 };
 static const SchemeEntry kSchemes[] = {
-    {1, 0, 0, launch_k1_1_0_0, launch_k2_1_0_0, occupancy_1_0_0}, {1, 1, 0, launch_k1_1_1_0, launch_k2_1_1_0, occupancy_1_1_0}, {2, 0, 0, launch_k1_2_0_0, launch_k2_2_0_0, occupancy_2_0_0},
-    {2, 1, 0, launch_k1_2_1_0, launch_k2_2_1_0, occupancy_2_1_0}, {2, 2, 0, launch_k1_2_2_0, launch_k2_2_2_0, occupancy_2_2_0}, {3, 0, 0, launch_k1_3_0_0, launch_k2_3_0_0, occupancy_3_0_0},
-    {3, 3, 0, launch_k1_3_3_0, launch_k2_3_3_0, occupancy_3_3_0},
-    {2, 1, 2, launch_k1_2_1_2, launch_k2_2_1_2, occupancy_2_1_2}, {3, 1, 3, launch_k1_3_1_3, launch_k2_3_1_3, occupancy_3_1_3},
+    {1, 0, 0, launch_k1_1_0_0, launch_k2_1_0_0, occupancy_1_0_0, launch_k1tc_1_0_0}, {1, 1, 0, launch_k1_1_1_0, launch_k2_1_1_0, occupancy_1_1_0, launch_k1tc_1_1_0}, {2, 0, 0, launch_k1_2_0_0, launch_k2_2_0_0, occupancy_2_0_0, launch_k1tc_2_0_0},
+    {2, 1, 0, launch_k1_2_1_0, launch_k2_2_1_0, occupancy_2_1_0, launch_k1tc_2_1_0}, {2, 2, 0, launch_k1_2_2_0, launch_k2_2_2_0, occupancy_2_2_0, launch_k1tc_2_2_0}, {3, 0, 0, launch_k1_3_0_0, launch_k2_3_0_0, occupancy_3_0_0, launch_k1tc_3_0_0},
+    {3, 3, 0, launch_k1_3_3_0, launch_k2_3_3_0, occupancy_3_3_0, launch_k1tc_3_3_0},
+    {2, 1, 2, launch_k1_2_1_2, launch_k2_2_1_2, occupancy_2_1_2, launch_k1tc_2_1_2}, {3, 1, 3, launch_k1_3_1_3, launch_k2_3_1_3, occupancy_3_1_3, launch_k1tc_3_1_3},
 };
 
 static thread_local char g_err[512] = "";
@@ -133,8 +138,22 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
         pl.ntc1 = 256;
         pl.T1 = pl.ntc1 * pl.P1 * pl.Q1 / hmax;
     }
-    if ((pl.T1 / pl.P1) % 8 != 0 || pl.T1 % pl.T != 0)
+    if (!pl.tc && ((pl.T1 / pl.P1) % 8 != 0 || pl.T1 % pl.T != 0))
         return fail(-3, "internal: forward tile %d unsupported (backward tile %d)", pl.T1, pl.T);
+    // tensor-core forward path (opt-in: PINNJET_TC=1): every hidden layer exactly 64 wide (padded), 2 or 4 jet channels
+    pl.tc = 0;
+    {
+        const char* env = getenv("PINNJET_TC");
+        bool ok = env && env[0] == '1' && (C == 2 || C == 4) && hmax == 64;
+        for (int n = 0; ok && n < sp.n_nets; ++n)
+            for (int h = 1; h < sp.net[n].n_linear; ++h) ok = ok && pl.hp[n][h] == 64;
+        if (ok && (256 / C) % pl.T == 0) {
+            pl.tc = 1;
+            pl.ntc1 = 256;
+            pl.T1 = 256 / C;
+            pl.P1 = pl.Q1 = 0;
+        }
+    }
     pl.RS1 = C * pl.T1 + ROW_PAD;
     pl.epi_batch = pl.T1 > 32 ? pl.T1 : 32;   // whole tiles; the program warp walks it 32 points at a time
     pl.n_tiles1 = (int)((N + pl.T1 - 1) / pl.T1);
@@ -164,6 +183,7 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
             const int hi = pl.hp[n][l], ho = pl.hp[n][l + 1];
             pl.b_wt[n][l] = big; big += (long long)hi * ho;
             pl.b_wo[n][l] = big; big += (long long)hi * ho;
+            pl.b_wimg[n][l] = big; big += 3 * 64 * 128 / 4;   // three bf16 images [64 x 64] (used by the tensor-core path)
             pl.chunks_fwd += (hi + CHUNK_FLOATS / ho - 1) / (CHUNK_FLOATS / ho);
             pl.chunks_bwd += (ho + CHUNK_FLOATS / hi - 1) / (CHUNK_FLOATS / hi);
         }
@@ -187,7 +207,26 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
     const int jet_bytes = hmax * pl.RS * 4;
     const int small_bytes = round_up(pl.small_floats * 4, 128);
     const int misc_bytes = 256;
-    {   // K1: act | ring | small | ycache | slots | misc | prog
+    if (pl.tc) {   // K1-TC: A images (3 x 32 KB, 1024-aligned at offset 0) | W images | small | ycache | slots | misc | ...
+        int n_hh = 0;
+        for (int n = 0; n < sp.n_nets; ++n) n_hh += sp.net[n].n_linear - 2;
+        const int nw = sp.n_nets * sp.wl;
+        int o = 0;
+        pl.k1_act = o; o += 3 * 256 * 128;
+        pl.k1_ring = o; o += n_hh * 3 * 64 * 128;
+        pl.k1_small = o; o += small_bytes;
+        pl.k1_ycache = o; o += 2 * sp.n_yrows * pl.epi_batch * 4;
+        pl.k1_slots = o; o += sp.n_slots * 32 * 4;
+        pl.k1_misc = o; o += misc_bytes;
+        pl.k1_wbuf = o; o += nw * pl.T1 * 4;
+        pl.k1_wslots = o; o += sp.wl > 0 ? sp.n_slots * 256 * 4 : 0;
+        pl.k1_prog = o; o += prog_len * 16;
+        pl.k1_progw = o; o += prog_w_len * 16;
+        pl.k1_bytes = o;
+        pl.n_stage = 1;
+        pl.resident_fwd = 1;
+        if (o > SMEM_LIMIT) return fail(-2, "tensor-core forward kernel does not fit in shared memory (%d B)", o);
+    } else {   // K1: act | ring | small | ycache | slots | misc | prog
         const int act_bytes = hmax * pl.RS1 * 4;
         const int ycache_bytes = 2 * sp.n_yrows * pl.epi_batch * 4, slots_bytes = sp.n_slots * 32 * 4;
         const int nw = sp.n_nets * sp.wl;
@@ -235,7 +274,7 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
     // ---- persistent grids: resident CTAs per SM x SMs, capped by the number of tiles ----
     {
         const SchemeEntry* e = find_scheme(sp.n1, sp.n2, sp.wl);
-        const int o1 = e->occ((pl.ntc1 == 256 && pl.Q1 == 4) ? 3 : 1, pl.ntc1, pl.k1_bytes), o2 = e->occ(2, pl.ntc, pl.k2_bytes);
+        const int o1 = pl.tc ? 1 : e->occ((pl.ntc1 == 256 && pl.Q1 == 4) ? 3 : 1, pl.ntc1, pl.k1_bytes), o2 = e->occ(2, pl.ntc, pl.k2_bytes);
         if (o1 < 1 || o2 < 1) return fail(-2, "kernel does not fit on an SM (occupancy %d / %d, smem %d / %d B)", o1, o2,
                                           pl.k1_bytes, pl.k2_bytes);
         pl.grid = pl.n_tiles1 < sms * o1 ? pl.n_tiles1 : sms * o1;
@@ -322,6 +361,20 @@ __global__ void pack_kernel(const __grid_constant__ PackArgs A, const float* __r
         }
         float* bp = pack + pl.s_b[n][l];
         for (int u = tid; u < ho; u += nt) bp[u] = (u < fout) ? b[u] : 0.0f;
+        if (hi == 64 && ho == 64) {   // tensor-core B operand: W[n][k] = w1 + w2 + w3 in bf16, K-major SWIZZLE_128B images
+            unsigned char* img = reinterpret_cast<unsigned char*>(pack + pl.b_wimg[n][l]);
+            for (int e = tid; e < 64 * 64; e += nt) {
+                const int r = e >> 6, k = e & 63;
+                float v = (r < fout && k < fin) ? W[r * fin + k] : 0.0f;
+                const size_t off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((((k * 2) >> 4) ^ (r & 7)) << 4) +
+                                   ((k * 2) & 15);
+                for (int t = 0; t < 3; ++t) {
+                    const __nv_bfloat16 hb = __float2bfloat16(v);
+                    *reinterpret_cast<__nv_bfloat16*>(img + (size_t)t * 8192 + off) = hb;
+                    v -= __bfloat162float(hb);
+                }
+            }
+        }
     }
     if (l == L) {
         const int hpL = pl.hp[n][L];
@@ -429,7 +482,7 @@ static int run_k1(const PjSpec* spec, const int32_t* prog, int32_t prog_len, con
     a.seeds = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_seed) : nullptr;
     a.wts = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_wts) : nullptr;
     const SchemeEntry* e = find_scheme(spec->n1, spec->n2, spec->wl);
-    if (int rc = check_cuda(e->k1(a, a.plan.grid, a.plan.k1_bytes, (cudaStream_t)stream), "forward launch")) return rc;
+    if (int rc = check_cuda((a.plan.tc ? e->k1tc : e->k1)(a, a.plan.grid, a.plan.k1_bytes, (cudaStream_t)stream), "forward launch")) return rc;
     if (sumsq_out)
         return check_cuda(launch_loss_finalize(a.loss_part, a.plan.grid, sumsq_out, (cudaStream_t)stream), "loss finalize");
     return 0;

@@ -51,6 +51,8 @@ struct Plan {
     int s_bout[PJ_MAX_NETS];
     long long b_wt[PJ_MAX_NETS][PJ_MAX_LINEAR];   // hidden->hidden Linear l: [in_p][out_p]  (forward B operand)
     long long b_wo[PJ_MAX_NETS][PJ_MAX_LINEAR];   //                          [out_p][in_p]  (adjoint B operand)
+    long long b_wimg[PJ_MAX_NETS][PJ_MAX_LINEAR];   // tensor-core path: 3 bf16 split images of W_l, K-major SWIZZLE_128B (float offset)
+    int tc;                              // 1: K1 runs the hidden-layer GEMMs on tcgen05 (pinnjet_k1tc.cuh)
     long long pack_floats;
     // ---- small-gradient accumulators in shared memory (float offsets) ----
     int g_w0[PJ_MAX_NETS], g_b[PJ_MAX_NETS][PJ_MAX_LINEAR], g_wl[PJ_MAX_NETS], g_bout[PJ_MAX_NETS], sgrad_floats;
