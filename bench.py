@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--points", type=int, default=0, help="points per GPU (default: the workload's BASELINE size)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--fit-epochs", type=int, default=200, help="epochs of the Solver.fit leg (0 = skip)")
+    ap.add_argument("--no-gpu-comparator", action="store_true", help="skip the torch-CUDA-autograd comparator leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -50,13 +52,14 @@ def parse():
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference closure (only place outside tests/ that executes oracle/)
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_reference_throughput(key, n_points, seconds, dtype=torch.float64, max_steps=None, warmup=1):
+def _oracle_step_fn(key, n_points, dtype, device="cpu"):
+    """One reference closure (solvers.py:369-395) through the oracle port: host coordinates in, loss (host float) out."""
     from oracle import reference_port as oracle
     wl = workloads.build(oracle.NAMESPACE, key)
     torch.manual_seed(0)
     nets, conds = wl.make_nets(), wl.make_conditions()
     for m in oracle.distinct_modules(nets):
-        m.to(dtype)
+        m.to(device=device, dtype=dtype)
     coords_np = workloads.sample_coords(wl, n_points, seed=0)
     eqs = workloads.bundle_eq_wrapper(wl)
 
@@ -64,9 +67,35 @@ def cpu_reference_throughput(key, n_points, seconds, dtype=torch.float64, max_st
         for m in oracle.distinct_modules(nets):
             for p in m.parameters():
                 p.grad = None
-        coords = [torch.as_tensor(c, dtype=dtype).reshape(-1, 1).requires_grad_(True) for c in coords_np]
+        coords = [torch.as_tensor(c, dtype=dtype).to(device).reshape(-1, 1).requires_grad_(True) for c in coords_np]
         _, _, loss = oracle.closure(nets, conds, eqs, coords, backward=True)
         return float(loss.detach())
+    return step
+
+
+def gpu_autograd_comparator(key, n_points, dev, seconds=2.0):
+    """Secondary comparator: the SAME reference algorithm on the SAME GPU through stock PyTorch CUDA
+    autograd (what a user of the reference gets on a B200 today).  Baseline only, measured after the timed region."""
+    out = {}
+    for name, dtype in (("f32", torch.float32), ("f64", torch.float64)):
+        step = _oracle_step_fn(key, n_points, dtype, device=dev)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        times, t_end = [], time.perf_counter() + seconds
+        while time.perf_counter() < t_end or len(times) < 3:
+            t0 = time.perf_counter()
+            step()                      # ends with a host read of the loss, like the reference closure (:394)
+            times.append(time.perf_counter() - t0)
+        med = float(np.median(times))
+        out[name] = {"value": n_points / med, "unit": "points/s", "ms_per_step": med * 1e3, "steps": len(times)}
+    out["what"] = (f"oracle/reference_port.py closure on cuda via torch {torch.__version__} autograd (eager), "
+                   f"{n_points} points, wall clock incl. the per-step loss read")
+    return out
+
+
+def cpu_reference_throughput(key, n_points, seconds, dtype=torch.float64, max_steps=None, warmup=1):
+    step = _oracle_step_fn(key, n_points, dtype)
 
     # "all the host threads it can use": torch's intra-op pool degrades badly when oversubscribed on these small
     # matrices (128 threads: 18 s/closure on the GPU box vs 0.12 s with 8), so the reference arm gets the thread count
@@ -176,6 +205,52 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(r for r in self.reasons if r != "gpu_idle"),
                 "power_w_max": max(self.power) if self.power else None, "samples": len(self.samples)}
+
+
+def _survey_generator(key, n, G):
+    """Training generators of SURVEY.md §8d for the five workloads (host sampling, fresh points every epoch)."""
+    if key == "c1":
+        return G.Generator1D(n, 0.1, 12.0, "equally-spaced-noisy")
+    if key in ("c2", "c3"):
+        side = int(round(n ** 0.5))
+        lo, hi = ((0.0, 0.0), (1.0, 1.0)) if key == "c2" else ((-1.0, 0.0), (1.0, 1.0))
+        return G.Generator2D((side, side), lo, hi, "equally-spaced-noisy")
+    if key == "c4":
+        return G.GeneratorSpherical(n, 0.1, 3.0)
+    if key == "c5":
+        rng = ((0.0, 2 * np.pi), (0.05, 0.5), (0.5, 2.0), (-1.0, 1.0), (-1.0, 1.0))
+        gens = [G.Generator1D(n, lo, hi, "uniform") for lo, hi in rng]
+        g = gens[0]
+        for h in gens[1:]:
+            g = g * h
+        return g
+    raise KeyError(key)
+
+
+def fit_throughput(key, n, epochs, warm=20):
+    """End-to-end ``Solver.fit`` of the product (SURVEY.md §8d "fit() epochs/s"): host sampling of a fresh batch, staging +
+    H2D, K0..K2b (one graph replay), torch Adam, one loss read per epoch; no validation batches (n_batches_valid=0)."""
+    from neurodiffeq_b200 import solvers as S, generators as G
+    nd = __import__("helpers").product_namespace()
+    wl = workloads.build(nd, key)
+    torch.manual_seed(0)
+    nets, conds = wl.make_nets(), wl.make_conditions()
+    gen = _survey_generator(key, n, G)
+    kw = dict(nets=nets, train_generator=gen, valid_generator=gen, n_batches_valid=0)
+    if wl.solver == "BundleSolver1D":
+        kw["eq_param_index"] = wl.eq_param_index
+    solver = getattr(S, wl.solver)(wl.diff_eqs, conds, **kw)
+    solver.fit(warm, tqdm_file=None)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    solver.fit(epochs, tqdm_file=None)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    hist = solver.metrics_history["train_loss"]
+    return {"epochs_per_s": epochs / dt, "points_per_s": epochs * gen.size / dt, "ms_per_epoch": dt / epochs * 1e3,
+            "epochs": epochs, "points_per_epoch": int(gen.size), "loss_first": hist[0], "loss_last": hist[-1],
+            "what": f"{wl.solver}.fit: host sampling ({type(gen).__name__}) + H2D + K0..K2b + torch Adam + 1 loss read "
+                    f"per epoch, n_batches_valid=0, wall clock"}
 
 
 def executed_flops(wl, tp):
@@ -373,11 +448,15 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get(args.workload, {}).get("k1_dram_bytes")
+    tc_on = os.environ.get("PINNJET_TC", "0") == "1"
     roofline = {
-        "kernel": "k1_forward_kernel (forward + jets + residual program)", "bound": "tensor", "achieved": ach_k1,
+        "kernel": ("k1tc_forward_kernel" if tc_on else "k1_forward_kernel") + " (forward + jets + residual program)",
+        "bound": "tensor", "achieved": ach_k1,
         "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach_k1 / bf16_peak, "traffic": traffic,
         "peak_source": f"dense bf16 tensor, {peak_src}",
-        "pipe": "fp32 FFMA2 on CUDA cores (fp32 parity; tensor cores would need 3xTF32 split, see DESIGN.md)",
+        "pipe": ("tcgen05 bf16x3 split (6 MMAs per fp32 product), fp32 TMEM accumulators (PINNJET_TC=1)" if tc_on else
+                 "fp32 FFMA2 on CUDA cores (fp32 parity; the bf16x3 tcgen05 forward kernel is opt-in, PINNJET_TC=1, "
+                 "see DESIGN.md)"),
         "fp32_ffma_peak": fp32_peak, "frac_of_fp32_ffma_peak": ach_k1 / fp32_peak,
         "algorithmic_flops_per_point": wl.flops_fwdjet, "launch_ms": k1_ms, "launch_ms_min": k1_min,
         # `achieved` counts the CANONICAL jet FLOPs (one channel per needed partial derivative).  When the
@@ -390,8 +469,18 @@ def main():
                "frac_of_fp32_ffma_peak": 2 * flops_k1 / (k2_ms * 1e-3) / 1e12 / fp32_peak},
     }
 
-    cpu_base = None
+    cpu_base, fit, gpu_cmp = None, None, None
     if rank == 0 and world == 1:
+        if args.fit_epochs > 0:
+            try:
+                fit = fit_throughput(args.workload, n, args.fit_epochs)
+            except Exception as e:  # the fit leg is a secondary report: never lose the bench line over it
+                fit = {"error": f"{type(e).__name__}: {e}"}
+        if not args.no_gpu_comparator:
+            try:
+                gpu_cmp = gpu_autograd_comparator(args.workload, n, dev)
+            except Exception as e:
+                gpu_cmp = {"error": f"{type(e).__name__}: {e}"}
         cpu_base = cpu_reference_throughput(args.workload, n, seconds=args.cpu_seconds)
         cpu_base = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
@@ -410,6 +499,7 @@ def main():
                     "d2h_bytes_per_step": 4},
             "gpu_launches": ours_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
+            "fit": fit, "gpu_autograd_baseline": gpu_cmp,
             "loss": loss, "wall_s_timed_region": t_wall,
             "step_ms_stats": {"min": float(step_ms.min()), "median": float(np.median(step_ms)),
                               "max": float(step_ms.max())},
