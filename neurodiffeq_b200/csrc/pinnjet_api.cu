@@ -144,11 +144,12 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
     pl.tc = 0;
     {
         const char* env = getenv("PINNJET_TC");
-        bool ok = env && env[0] == '1' && (C == 2 || C == 4) && hmax == 64;
+        const int level = (env && (env[0] == '1' || env[0] == '2') && env[1] == 0) ? env[0] - '0' : 0;   // 2: transposed epilogue
+        bool ok = level > 0 && (C == 2 || C == 4) && hmax == 64;
         for (int n = 0; ok && n < sp.n_nets; ++n)
             for (int h = 1; h < sp.net[n].n_linear; ++h) ok = ok && pl.hp[n][h] == 64;
         if (ok && (256 / C) % pl.T == 0) {
-            pl.tc = 1;
+            pl.tc = level;
             pl.ntc1 = 256;
             pl.T1 = 256 / C;
             pl.P1 = pl.Q1 = 0;
@@ -213,7 +214,7 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
         const int nw = sp.n_nets * sp.wl;
         int o = 0;
         pl.k1_act = o; o += 3 * 256 * 128;
-        pl.k1_ring = o; o += n_hh * 3 * 64 * 128;
+        pl.k1_ring = o; o += n_hh * 3 * 64 * 128 + (pl.tc == 2 ? sp.n_nets * 3 * 16 * 128 : 0);   // + output-layer images
         pl.k1_small = o; o += small_bytes;
         pl.k1_ycache = o; o += 2 * sp.n_yrows * pl.epi_batch * 4;
         pl.k1_slots = o; o += sp.n_slots * 32 * 4;

@@ -52,7 +52,7 @@ struct Plan {
     long long b_wt[PJ_MAX_NETS][PJ_MAX_LINEAR];   // hidden->hidden Linear l: [in_p][out_p]  (forward B operand)
     long long b_wo[PJ_MAX_NETS][PJ_MAX_LINEAR];   //                          [out_p][in_p]  (adjoint B operand)
     long long b_wimg[PJ_MAX_NETS][PJ_MAX_LINEAR];   // tensor-core path: 3 bf16 split images of W_l, K-major SWIZZLE_128B (float offset)
-    int tc;                              // 1: K1 runs the hidden-layer GEMMs on tcgen05 (pinnjet_k1tc.cuh)
+    int tc;                              // 1 / 2: K1 runs the hidden-layer GEMMs on tcgen05 (pinnjet_k1tc.cuh / _k1tc2.cuh)
     long long pack_floats;
     // ---- small-gradient accumulators in shared memory (float offsets) ----
     int g_w0[PJ_MAX_NETS], g_b[PJ_MAX_NETS][PJ_MAX_LINEAR], g_wl[PJ_MAX_NETS], g_bout[PJ_MAX_NETS], sgrad_floats;

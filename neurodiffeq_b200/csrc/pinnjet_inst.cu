@@ -1,7 +1,7 @@
 // pinnjet_inst.cu -- one translation unit per jet-channel scheme: compiled with -DPJ_N1=.. -DPJ_N2=.. (see build.py).
 // PJ_N1 = PJ_N2 = -1 builds the scheme-independent helpers (K2b reduce, loss finalize).
 #include "pinnjet_k2.cuh"
-#include "pinnjet_k1tc.cuh"
+#include "pinnjet_k1tc2.cuh"
 
 #ifndef PJ_WL
 #define PJ_WL 0
@@ -109,6 +109,13 @@ cudaError_t PJ_NAME(launch_k2_, PJ_N1, PJ_N2)(const K2Args& a, int grid, int sme
 // tensor-core forward kernel (2 or 4 jet channels, 64-wide hidden layers); returns cudaErrorNotSupported otherwise
 cudaError_t PJ_NAME(launch_k1tc_, PJ_N1, PJ_N2)(const K1Args& a, int grid, int smem, cudaStream_t s) {
     if constexpr (kC == 2 || kC == 4) {
+        if (a.plan.tc == 2) {   // transposed-epilogue variant (pinnjet_k1tc2.cuh)
+            static int c2 = 0;
+            auto kern2 = k1tc2_forward_kernel<PJ_N1, PJ_N2, PJ_WL>;
+            if (cudaError_t e = configure(kern2, c2)) return e;
+            kern2<<<grid, 576, smem, s>>>(a);
+            return cudaGetLastError();
+        }
         static int c = 0;
         auto kern = k1tc_forward_kernel<PJ_N1, PJ_N2, PJ_WL>;
         if (cudaError_t e = configure(kern, c)) return e;
