@@ -12,9 +12,9 @@ User-supplied boundary callables (``x_min_val=lambda y: torch.sin(np.pi*y)`` ...
 
 Implemented: NoCondition :205-222, IVP :225-267, BundleIVP :270-345, DirichletBVP :398-435,
 BundleDirichletBVP :348-395, DirichletBVP2D :438-509, IBVP1D Dirichlet-Dirichlet :661-681,
-DirichletBVPSpherical :887-956, InfDirichletBVPSpherical :960-1019.  The Neumann flavours of IBVP1D / DoubleEndedBVP1D
-evaluate the network at boundary points (conditions.py:685-712) -- a second forward pass at other coordinates, not yet
-in the kernels -- and raise NotImplementedError.
+IBVP1D with Neumann data :670-701, DoubleEndedBVP1D :715-883, DirichletBVPSpherical :887-956,
+InfDirichletBVPSpherical :960-1019.  The Neumann flavours evaluate the network AT a boundary abscissa
+(conditions.py:585-596, 823-834): traced as a second instance of the same network fed by a constant coordinate.
 """
 import warnings
 
@@ -181,8 +181,19 @@ class DirichletBVP2D(BaseCondition):
         return a_xy + xt * (1 - xt) * yt * (1 - yt) * output_tensor
 
 
+def _boundary_leaf(ref, value):
+    """The reference's ``value * torch.ones_like(ref, requires_grad=True)`` (conditions.py:585-596, 823-834): a fresh leaf
+    holding a boundary abscissa, at which the network is evaluated and differentiated.  Traced: a constant coordinate."""
+    if _sym.is_symbolic(ref):
+        return ref.g.const_coord(value)
+    return value * torch.ones_like(ref, requires_grad=True)
+
+
 class IBVP1D(BaseCondition):
-    """u(x,t0)=u0(x) with Dirichlet data g(t), h(t) at x0, x1 (reference conditions.py:512-712, DD branch)."""
+    """u(x,t0)=u0(x) with Dirichlet or Neumann data at x0 and x1 (reference conditions.py:512-712; the four branches
+    DD :661-666, DN :670-676, ND :680-686, NN :689-701).  The Neumann branches evaluate the network (and its x-derivative)
+    at the boundary abscissa: in the fused path that is a second instance of the same network fed by a constant
+    coordinate, sharing the weights (and accumulating into the same gradient)."""
 
     def __init__(self, x_min, x_max, t_min, t_min_val, x_min_val=None, x_min_prime=None, x_max_val=None,
                  x_max_prime=None):
@@ -195,19 +206,93 @@ class IBVP1D(BaseCondition):
         self.t_min, self.t_min_val = t_min, t_min_val
 
     def enforce(self, net, x, t):
-        if not (self.x_min_val and self.x_max_val):
-            raise NotImplementedError(
-                "IBVP1D with Neumann data evaluates the network at the boundary (reference conditions.py:685-712); "
-                "only the Dirichlet-Dirichlet form is implemented in the fused kernels")
-        out, _ = self._network_output(net, x, t)
-        return self.parameterize(out, x, t)
+        uxt, _ = self._network_output(net, x, t)
+        if self.x_min_val and self.x_max_val:
+            return self.parameterize(uxt, x, t)
+        elif self.x_min_val and self.x_max_prime:
+            x1 = _boundary_leaf(x, self.x_max)
+            return self.parameterize(uxt, x, t, self._network_output(net, x1, t)[0], x1)
+        elif self.x_min_prime and self.x_max_val:
+            x0 = _boundary_leaf(x, self.x_min)
+            return self.parameterize(uxt, x, t, self._network_output(net, x0, t)[0], x0)
+        elif self.x_min_prime and self.x_max_prime:
+            x0, x1 = _boundary_leaf(x, self.x_min), _boundary_leaf(x, self.x_max)
+            return self.parameterize(uxt, x, t, self._network_output(net, x0, t)[0], x0,
+                                     self._network_output(net, x1, t)[0], x1)
+        raise NotImplementedError("Sorry, this boundary condition is not implemented.")
 
     def parameterize(self, u, x, t, *additional_tensors):
+        from .neurodiffeq import diff
         t0 = t.g.const(self.t_min) if _sym.is_symbolic(t) else torch.full_like(t, self.t_min)
         xt = (x - self.x_min) / (self.x_max - self.x_min)
-        a_xt = self.t_min_val(x) + xt * (self.x_max_val(t) - self.x_max_val(t0)) \
-            + (1 - xt) * (self.x_min_val(t) - self.x_min_val(t0))
-        return a_xt + xt * (1 - xt) * (1 - _exp(-(t - self.t_min))) * u
+        span = self.x_max - self.x_min
+        decay = 1 - _exp(-(t - self.t_min))
+        if self.x_min_val and self.x_max_val:
+            a_xt = self.t_min_val(x) + xt * (self.x_max_val(t) - self.x_max_val(t0)) \
+                + (1 - xt) * (self.x_min_val(t) - self.x_min_val(t0))
+            return a_xt + xt * (1 - xt) * decay * u
+        if self.x_min_val and self.x_max_prime:
+            ux1t, x1 = additional_tensors
+            a_xt = (self.x_min_val(t) - self.x_min_val(t0)) + self.t_min_val(x) \
+                + xt * span * (self.x_max_prime(t) - self.x_max_prime(t0))
+            return a_xt + xt * decay * (u - span * diff(ux1t, x1) - ux1t)
+        if self.x_min_prime and self.x_max_val:
+            ux0t, x0 = additional_tensors
+            a_xt = (self.x_max_val(t) - self.x_max_val(t0)) + self.t_min_val(x) \
+                + (xt - 1) * span * (self.x_min_prime(t) - self.x_min_prime(t0))
+            return a_xt + (1 - xt) * decay * (u + span * diff(ux0t, x0) - ux0t)
+        ux0t, x0, ux1t, x1 = additional_tensors
+        a_xt = self.t_min_val(x) - 0.5 * (1 - xt) ** 2 * span * (self.x_min_prime(t) - self.x_min_prime(t0)) \
+            + 0.5 * xt ** 2 * span * (self.x_max_prime(t) - self.x_max_prime(t0))
+        return a_xt + decay * (u - xt * span * diff(ux0t, x0) + 0.5 * xt ** 2 * span * (diff(ux0t, x0) - diff(ux1t, x1)))
+
+
+class DoubleEndedBVP1D(BaseCondition):
+    """u or u' prescribed at both ends of [x0, x1] (reference conditions.py:715-883; the formulas follow the reference
+    CODE :857-883, which differs from its docstring in the Neumann branches).  Neumann ends evaluate the network at the
+    boundary abscissa, see :class:`IBVP1D`."""
+
+    def __init__(self, x_min, x_max, x_min_val=None, x_min_prime=None, x_max_val=None, x_max_prime=None):
+        super().__init__()
+        n_conditions = sum(c is not None for c in [x_min_val, x_min_prime, x_max_val, x_max_prime])
+        if n_conditions != 2 or (x_min_val and x_min_prime) or (x_max_val and x_max_prime):
+            raise NotImplementedError("Sorry, this boundary condition is not implemented.")
+        self.x_min, self.x_min_val, self.x_min_prime = x_min, x_min_val, x_min_prime
+        self.x_max, self.x_max_val, self.x_max_prime = x_max, x_max_val, x_max_prime
+
+    def enforce(self, net, x):
+        ux, _ = self._network_output(net, x)
+        if self.x_min_val is not None and self.x_max_val is not None:
+            return self.parameterize(ux, x)
+        elif self.x_min_val is not None and self.x_max_prime is not None:
+            x1 = _boundary_leaf(x, self.x_max)
+            return self.parameterize(ux, x, self._network_output(net, x1)[0], x1)
+        elif self.x_min_prime is not None and self.x_max_val is not None:
+            x0 = _boundary_leaf(x, self.x_min)
+            return self.parameterize(ux, x, self._network_output(net, x0)[0], x0)
+        elif self.x_min_prime is not None and self.x_max_prime is not None:
+            x0, x1 = _boundary_leaf(x, self.x_min), _boundary_leaf(x, self.x_max)
+            return self.parameterize(ux, x, self._network_output(net, x0)[0], x0, self._network_output(net, x1)[0], x1)
+        raise NotImplementedError("Sorry, this boundary condition is not implemented.")
+
+    def parameterize(self, u, x, *additional_tensors):
+        from .neurodiffeq import diff
+        xt = (x - self.x_min) / (self.x_max - self.x_min)
+        span = self.x_max - self.x_min
+        if self.x_min_val is not None and self.x_max_val is not None:
+            return self.x_min_val * (1 - xt) + self.x_max_val * xt + xt * (1 - xt) * u
+        if self.x_min_val is not None and self.x_max_prime is not None:
+            ux1, x1 = additional_tensors
+            a_x = (1 - xt) * self.x_min_val + 0.5 * xt ** 2 * self.x_max_prime * span
+            return a_x + xt * (u - ux1 + self.x_min_val - diff(ux1, x1) * span)
+        if self.x_min_prime is not None and self.x_max_val is not None:
+            ux0, x0 = additional_tensors
+            a_x = xt * self.x_max_val - 0.5 * (1 - xt) ** 2 * self.x_min_prime * span
+            return a_x + (1 - xt) * (u - ux0 + self.x_max_val + diff(ux0, x0) * span)
+        ux0, x0, ux1, x1 = additional_tensors
+        a_x = -0.5 * (1 - xt) ** 2 * span * self.x_min_prime + 0.5 * xt ** 2 * span * self.x_max_prime
+        return a_x + 0.5 * xt ** 2 * (u - ux1 - 0.5 * diff(ux1, x1) * span) \
+            + 0.5 * (1 - xt) ** 2 * (u - ux0 + 0.5 * diff(ux0, x0) * span)
 
 
 class DirichletBVPSpherical(BaseCondition):

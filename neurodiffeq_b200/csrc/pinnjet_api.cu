@@ -25,6 +25,7 @@ PJ_DECL(3, 0, 0)
 PJ_DECL(3, 3, 0)
 PJ_DECL(2, 1, 2)   // combined second-order channel over 2 / 3 weighted directions
 PJ_DECL(3, 1, 3)
+PJ_DECL(4, 1, 4)   // 4 directions (e.g. x, t, a boundary abscissa and one polarisation direction), combined only
 #undef PJ_DECL
 cudaError_t launch_reduce(const float* gpart, int n_parts, long long n_theta, float* grad, cudaStream_t s);
 cudaError_t launch_loss_finalize(const float* part, int n_parts, float* out, cudaStream_t s);
@@ -43,6 +44,7 @@ static const SchemeEntry kSchemes[] = {
     {2, 1, 0, launch_k1_2_1_0, launch_k2_2_1_0, occupancy_2_1_0, launch_k1tc_2_1_0}, {2, 2, 0, launch_k1_2_2_0, launch_k2_2_2_0, occupancy_2_2_0, launch_k1tc_2_2_0}, {3, 0, 0, launch_k1_3_0_0, launch_k2_3_0_0, occupancy_3_0_0, launch_k1tc_3_0_0},
     {3, 3, 0, launch_k1_3_3_0, launch_k2_3_3_0, occupancy_3_3_0, launch_k1tc_3_3_0},
     {2, 1, 2, launch_k1_2_1_2, launch_k2_2_1_2, occupancy_2_1_2, launch_k1tc_2_1_2}, {3, 1, 3, launch_k1_3_1_3, launch_k2_3_1_3, occupancy_3_1_3, launch_k1tc_3_1_3},
+    {4, 1, 4, launch_k1_4_1_4, launch_k2_4_1_4, occupancy_4_1_4, launch_k1tc_4_1_4},
 };
 
 static thread_local char g_err[512] = "";

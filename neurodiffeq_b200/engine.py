@@ -17,8 +17,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.environ.get("PINNJET_LIB", os.path.join(_HERE, "csrc", "libpinnjet.so"))
 
 PJ_MAX_NETS, PJ_MAX_LINEAR, PJ_MAX_COORDS, PJ_MAX_DIRS = 4, 8, 8, 4
-SUPPORTED_SCHEMES = [(1, 0), (1, 1), (2, 0), (2, 1), (2, 2), (3, 0), (3, 3)]
-COMBINED_SCHEMES = [(2, 2), (3, 3)]   # (n1, n2) that also exist with ONE weighted second-order channel (wl = n2)
+SUPPORTED_SCHEMES = [(1, 0), (1, 1), (2, 0), (2, 1), (2, 2), (3, 0), (3, 3), (4, 4)]
+COMBINED_SCHEMES = [(2, 2), (3, 3), (4, 4)]   # (n1, n2) that also exist with ONE weighted second-order channel (wl = n2)
+COMBINED_ONLY = [(4, 4)]                      # ... and these exist ONLY in that form (9 separate channels do not fit)
 
 
 def combine_seconds(n1, n2):
@@ -116,7 +117,14 @@ class FusedProblem:
         self.tp = TracedProblem(nets, conditions, diff_eqs, n_coords, coords_for_condition, pad_scheme=pad_scheme,
                                 combine_seconds=combine_seconds)
         tp = self.tp
-        self.n_coords, self.n_funcs, self.n_eq = n_coords, tp.n_funcs, tp.n_eq
+        if (tp.scheme.n1, tp.scheme.n2) in COMBINED_ONLY and not tp.wl:
+            raise NotImplementedError(
+                f"jet channels (n1={tp.scheme.n1}, n2={tp.scheme.n2}) are only compiled with ONE combined second-order "
+                f"channel, which needs residuals affine in the second derivatives with coordinate-only coefficients")
+        if tp.n_coords > PJ_MAX_COORDS:
+            raise NotImplementedError(f"{tp.n_coords} coordinates incl. boundary abscissae (max {PJ_MAX_COORDS})")
+        self.n_coords, self.n_funcs, self.n_eq = n_coords, tp.n_funcs, tp.n_eq   # n_coords: SAMPLED coordinates (user-facing)
+        self._const_coord_cache = {}
         self._adopt_parameters()
         self._build_spec()
         dev = self.device
@@ -133,10 +141,13 @@ class FusedProblem:
 
     # ---- parameters: one flat fp32 buffer, nn.Parameters become views (torch layout preserved) ----------------------
     def _adopt_parameters(self):
-        params = []
-        for nd in self.tp.nets:
+        params, seen = [], set()
+        for nd in self.tp.nets:   # a module evaluated at two coordinate lists (boundary instance) owns ONE set of weights
             nd.module.to(device=self.device, dtype=torch.float32)
-            params += nd.parameters()
+            for p in nd.parameters():
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    params.append(p)
         n_theta = sum(p.numel() for p in params)
         self.theta = torch.empty(n_theta, dtype=torch.float32, device=self.device)
         # one buffer [grad_theta | sum r^2] so that a multi-GPU step needs a single all-reduce
@@ -155,6 +166,7 @@ class FusedProblem:
                 off += n
         self.params = params
         self.n_theta = n_theta
+        self._offset_of = {id(p): o for p, o in zip(params, self.offsets)}
 
     def parameters_linked(self):
         """True while every nn.Parameter still aliases the flat buffers (``net.to()`` / re-assignment break it)."""
@@ -197,7 +209,6 @@ class FusedProblem:
         sp.n_slots = max(tp.prog_eval.n_slots, tp.prog_train.n_slots, tp.prog_train_ext.n_slots,
                          tp.prog_w.n_slots if tp.wl else 1)
         sp.n_theta = self.n_theta
-        k = 0
         for n, nd in enumerate(tp.nets):
             net = sp.net[n]
             net.n_in = nd.widths[0]
@@ -210,10 +221,9 @@ class FusedProblem:
                 net.width[i] = w
             net.act = nd.act
             net.yrow0 = tp.yrow0[n]
-            for l in range(net.n_linear):
-                net.w_off[l] = self.offsets[k]
-                net.b_off[l] = self.offsets[k + 1]
-                k += 2
+            for l, lin in enumerate(nd.linears):
+                net.w_off[l] = self._offset_of[id(lin.weight)]
+                net.b_off[l] = self._offset_of[id(lin.bias)]
         self.spec = sp
 
     @property
@@ -248,7 +258,7 @@ class FusedProblem:
     def _coord_ptrs(self, coords, n_points):
         if len(coords) != self.n_coords:
             raise ValueError(f"expected {self.n_coords} coordinate vectors, got {len(coords)}")
-        arr = (ctypes.c_void_p * self.n_coords)()
+        arr = (ctypes.c_void_p * self.tp.n_coords)()
         keep = []
         for i, c in enumerate(coords):
             if c.device != self.device or c.dtype != torch.float32 or not c.is_contiguous() or c.numel() != n_points:
@@ -257,6 +267,13 @@ class FusedProblem:
                     raise ValueError("all coordinate vectors must have the same number of points")
             keep.append(c)
             arr[i] = c.data_ptr()
+        if self.tp.const_coords:   # constant coordinates (network evaluated at a boundary): filled arrays, cached per size
+            consts = self._const_coord_cache.get(n_points)
+            if consts is None:
+                consts = [torch.full((n_points,), v, dtype=torch.float32, device=self.device) for v in self.tp.const_coords]
+                self._const_coord_cache[n_points] = consts
+            for k, c in enumerate(consts):
+                arr[self.n_coords + k] = c.data_ptr()
         return arr, keep
 
     def _prog_w_args(self):

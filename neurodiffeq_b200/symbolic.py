@@ -51,6 +51,8 @@ class Graph:
         self.nodes = []
         self.nets = []  # list of (module, in_coord tuple)
         self._net_ids = {}
+        self.n_sampled = None   # number of sampled coordinates (set by the tracer); constant coordinates follow them
+        self.const_coords = []  # values of the constant ("virtual") coordinates n_sampled, n_sampled + 1, ...
 
     def _mk(self, op, args=(), imm=None):
         key = (op, tuple(a.idx for a in args), imm)
@@ -68,6 +70,18 @@ class Graph:
     def coord(self, i):
         return self._mk("coord", (), int(i))
 
+    def const_coord(self, value):
+        """A coordinate leaf that has the same value at every sample point: what the reference builds with
+        ``x1 = x_max * torch.ones_like(x, requires_grad=True)`` (conditions.py:585, 823) to evaluate -- and differentiate --
+        the network AT a boundary.  It is a genuine extra coordinate of the traced problem: ``diff(net(x1, t), x1)`` is
+        the derivative w.r.t. that network input, and nothing else depends on it."""
+        if self.n_sampled is None:
+            raise RuntimeError("constant coordinates can only be created while a problem is being traced")
+        value = float(value)
+        if value not in self.const_coords:
+            self.const_coords.append(value)
+        return self.coord(self.n_sampled + self.const_coords.index(value))
+
     def net(self, n, o, alpha=()):
         return self._mk("net", (), (int(n), int(o), tuple(sorted(alpha))))
 
@@ -83,9 +97,7 @@ class Graph:
 
     def register_net(self, module, in_coord):
         key = (id(module), tuple(in_coord))
-        if key not in self._net_ids:
-            if any(id(m) == id(module) and ic != tuple(in_coord) for m, ic in self.nets):
-                raise NotImplementedError("the same network is evaluated at two different coordinate lists")
+        if key not in self._net_ids:   # the same module at another coordinate list is another instance sharing its weights
             self._net_ids[key] = len(self.nets)
             self.nets.append((module, tuple(in_coord)))
         return self._net_ids[key]

@@ -81,7 +81,8 @@ class TracedProblem:
         (reference solvers.py:894-916)."""
         g = S.Graph()
         self.graph = g
-        self.n_coords = n_coords
+        g.n_sampled = n_coords
+        self.n_sampled = n_coords
         coords = [g.coord(i) for i in range(n_coords)]
         funcs = []
         for k, (net, cond) in enumerate(zip(nets, conditions)):
@@ -91,6 +92,11 @@ class TracedProblem:
         if isinstance(res, S.Sym) or not hasattr(res, "__len__"):
             res = [res]
         residuals = [g.lift(r) for r in res]
+        # constant coordinates created by the conditions (network evaluated at a boundary) follow the sampled ones; for the
+        # kernels they are ordinary coordinate arrays (filled with the constant by the engine)
+        self.const_coords = tuple(g.const_coords)
+        n_coords = self.n_sampled + len(self.const_coords)
+        self.n_coords = n_coords
         self.n_funcs, self.n_eq = len(funcs), len(residuals)
         self.nets = [NetDescription(m, ic) for m, ic in g.nets]
         if not self.nets:
@@ -214,6 +220,14 @@ class TracedProblem:
         if self._prog_train_ext is None:
             self._prog_train_ext = self._train_program(external_rbar=True)
         return self._prog_train_ext
+
+    def extend_coords(self, coords):
+        """[n_sampled, N] sampled coordinates -> [n_coords, N] with the constant coordinate rows appended."""
+        coords = np.asarray(coords)
+        if coords.shape[0] == self.n_coords or not self.const_coords:
+            return coords
+        extra = np.repeat(np.asarray(self.const_coords, dtype=coords.dtype)[:, None], coords.shape[1], axis=1)
+        return np.concatenate([coords, extra], axis=0)
 
     def direction_matrix(self):
         """[n1, n_coords] float32: direction vectors of the first-order channels."""

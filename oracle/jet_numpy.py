@@ -112,10 +112,11 @@ def backward(weights, act, x_in, dirs_in, n2, z_store, ybar, wl=None):
 def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True):
     """Evaluate a TracedProblem end to end in float64.
 
-    ``params_per_net``: list (per distinct net) of [W0,b0,W1,b1,...] numpy arrays (torch layout).
-    Returns dict(u, residual, loss, grads (flat list in the same order), y, seeds, z_store)."""
+    ``params_per_net``: list (per network INSTANCE of ``tp.nets``; instances of one module get the same arrays) of
+    [W0,b0,W1,b1,...] numpy arrays (torch layout).
+    Returns dict(u, residual, loss, grads (flat list per distinct MODULE, instances summed), y, seeds, z_store)."""
     from neurodiffeq_b200 import symbolic as S
-    coords = np.asarray(coords, dtype=np.float64)
+    coords = tp.extend_coords(np.asarray(coords, dtype=np.float64))   # + constant coordinates (boundary instances)
     N = coords.shape[1]
     dirs = np.asarray(tp.scheme.dirs, dtype=np.float64).reshape(tp.scheme.n1, tp.n_coords)
     n1, n2 = tp.scheme.n1, tp.scheme.n2
@@ -144,7 +145,7 @@ def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True):
         _, r2, seeds = S.evaluate_program(tp.prog_train, coords, y_rows, params=[scale], n_r=tp.n_eq,
                                           n_seed=tp.n_yrows)
         assert np.allclose(r2, r)
-        grads = []
+        by_module = {}   # instances that share a module (network evaluated at a boundary too) add up, like autograd
         for k, nd in enumerate(tp.nets):
             Ws, x_in, d_in, z_store, wl = stores[k]
             ybar = np.zeros((C, nd.n_out, N))
@@ -152,7 +153,13 @@ def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True):
                 for c in range(C):
                     ybar[c, o] = seeds[tp.yrow0[k] + o * C + c]
             gW, gb = backward(Ws, nd.act, x_in, d_in, n2, z_store, ybar, wl)
+            mine = []
             for w, b in zip(gW, gb):
-                grads += [w, b]
+                mine += [w, b]
+            acc = by_module.setdefault(id(nd.module), mine)
+            if acc is not mine:
+                for a, m in zip(acc, mine):
+                    a += m
+        grads = [g_ for gs in by_module.values() for g_ in gs]
         out.update(grads=grads, seeds=seeds, z_store=[s[3] for s in stores])
     return out

@@ -172,21 +172,108 @@ class DirichletBVP2D(_Condition):  # :438-509
         return a + xt * (1 - xt) * yt * (1 - yt) * out
 
 
-class IBVP1D(_Condition):  # :512-712, Dirichlet-Dirichlet branch only (:583, :661-666, :677-681)
+def _ann(cond, net, *cols):  # the local ``ANN`` helper of conditions.py:577-581 / :816-820
+    out = net(torch.cat(cols, dim=1))
+    if cond.ith_unit is not None:
+        out = out[:, cond.ith_unit].view(-1, 1)
+    return out
+
+
+def _which_ends(cond):  # branch selection by truthiness (IBVP1D :583-600) / by `is not None` (DoubleEndedBVP1D :822-840)
+    return ("d" if cond.lo_val_given else "n") + ("d" if cond.hi_val_given else "n")
+
+
+class IBVP1D(_Condition):  # :512-712 (enforce :559-600, parameterize :603-712)
     def __init__(self, x_min, x_max, t_min, t_min_val, x_min_val=None, x_min_prime=None, x_max_val=None,
                  x_max_prime=None):
         super().__init__()
-        if not (x_min_val and x_max_val) or x_min_prime or x_max_prime:
-            raise NotImplementedError("oracle covers the Dirichlet-Dirichlet IBVP1D only")
-        self.x_min, self.x_max, self.t_min = x_min, x_max, t_min
-        self.t_min_val, self.x_min_val, self.x_max_val = t_min_val, x_min_val, x_max_val
+        given = [c is not None for c in (x_min_val, x_min_prime, x_max_val, x_max_prime)]
+        if sum(given) != 2 or (x_min_val and x_min_prime) or (x_max_val and x_max_prime):   # :546-548
+            raise NotImplementedError("Sorry, this boundary condition is not implemented.")
+        self.x_min, self.x_max, self.t_min, self.t_min_val = x_min, x_max, t_min, t_min_val
+        self.x_min_val, self.x_min_prime, self.x_max_val, self.x_max_prime = x_min_val, x_min_prime, x_max_val, x_max_prime
+        self.lo_val_given, self.hi_val_given = bool(x_min_val), bool(x_max_val)
 
-    def parameterize(self, out, x, t):
-        t0 = torch.full_like(t, self.t_min)
-        xt = (x - self.x_min) / (self.x_max - self.x_min)
-        a = self.t_min_val(x) + xt * (self.x_max_val(t) - self.x_max_val(t0)) \
-            + (1 - xt) * (self.x_min_val(t) - self.x_min_val(t0))
-        return a + xt * (1 - xt) * (1 - torch.exp(-(t - self.t_min))) * out
+    def enforce(self, net, x, t):
+        u = _ann(self, net, x, t)
+        extra = []
+        kind = _which_ends(self)
+        if kind[0] == "n":   # network at the left boundary, on a fresh leaf so that d/dx0 can be taken (:590, :594)
+            x0 = self.x_min * torch.ones_like(x, requires_grad=True)
+            extra += [_ann(self, net, x0, t), x0]
+        if kind[1] == "n":   # ... and at the right boundary (:586, :595)
+            x1 = self.x_max * torch.ones_like(x, requires_grad=True)
+            extra += [_ann(self, net, x1, t), x1]
+        return self.parameterize(u, x, t, *extra)
+
+    def parameterize(self, out, x, t, *extra):
+        t0 = self.t_min * torch.ones_like(t, requires_grad=True)
+        s = (x - self.x_min) / (self.x_max - self.x_min)          # x tilde
+        tau = t - self.t_min                                       # t tilde
+        width = self.x_max - self.x_min
+        fade = 1 - torch.exp(-tau)
+        kind = _which_ends(self)
+        if kind == "dd":    # :661-666
+            a = self.t_min_val(x) + s * (self.x_max_val(t) - self.x_max_val(t0)) \
+                + (1 - s) * (self.x_min_val(t) - self.x_min_val(t0))
+            return a + s * (1 - s) * fade * out
+        if kind == "dn":    # :670-676
+            n1, x1 = extra
+            a = (self.x_min_val(t) - self.x_min_val(t0)) + self.t_min_val(x) \
+                + s * width * (self.x_max_prime(t) - self.x_max_prime(t0))
+            return a + s * fade * (out - width * diff(n1, x1) - n1)
+        if kind == "nd":    # :680-686
+            n0, x0 = extra
+            a = (self.x_max_val(t) - self.x_max_val(t0)) + self.t_min_val(x) \
+                + (s - 1) * width * (self.x_min_prime(t) - self.x_min_prime(t0))
+            return a + (1 - s) * fade * (out + width * diff(n0, x0) - n0)
+        n0, x0, n1, x1 = extra   # :689-701
+        a = self.t_min_val(x) - 0.5 * (1 - s) ** 2 * width * (self.x_min_prime(t) - self.x_min_prime(t0)) \
+            + 0.5 * s ** 2 * width * (self.x_max_prime(t) - self.x_max_prime(t0))
+        d0, d1 = diff(n0, x0), diff(n1, x1)
+        return a + fade * (out - s * width * d0 + 0.5 * s ** 2 * width * (d0 - d1))
+
+
+class DoubleEndedBVP1D(_Condition):  # :715-883 (enforce :797-840, formulas of the CODE :857-883)
+    def __init__(self, x_min, x_max, x_min_val=None, x_min_prime=None, x_max_val=None, x_max_prime=None):
+        super().__init__()
+        given = [c is not None for c in (x_min_val, x_min_prime, x_max_val, x_max_prime)]
+        if sum(given) != 2 or (x_min_val and x_min_prime) or (x_max_val and x_max_prime):   # :751-753
+            raise NotImplementedError("Sorry, this boundary condition is not implemented.")
+        self.x_min, self.x_max = x_min, x_max
+        self.x_min_val, self.x_min_prime, self.x_max_val, self.x_max_prime = x_min_val, x_min_prime, x_max_val, x_max_prime
+        self.lo_val_given, self.hi_val_given = x_min_val is not None, x_max_val is not None
+
+    def enforce(self, net, x):
+        u = _ann(self, net, x)
+        extra = []
+        kind = _which_ends(self)
+        if kind[0] == "n":
+            x0 = self.x_min * torch.ones_like(x, requires_grad=True)
+            extra += [_ann(self, net, x0), x0]
+        if kind[1] == "n":
+            x1 = self.x_max * torch.ones_like(x, requires_grad=True)
+            extra += [_ann(self, net, x1), x1]
+        return self.parameterize(u, x, *extra)
+
+    def parameterize(self, out, x, *extra):
+        s = (x - self.x_min) / (self.x_max - self.x_min)
+        width = self.x_max - self.x_min
+        kind = _which_ends(self)
+        if kind == "dd":    # :857-859
+            return self.x_min_val * (1 - s) + self.x_max_val * s + s * (1 - s) * out
+        if kind == "dn":    # :863-865
+            n1, x1 = extra
+            a = (1 - s) * self.x_min_val + 0.5 * s ** 2 * self.x_max_prime * width
+            return a + s * (out - n1 + self.x_min_val - diff(n1, x1) * width)
+        if kind == "nd":    # :871-873
+            n0, x0 = extra
+            a = s * self.x_max_val - 0.5 * (1 - s) ** 2 * self.x_min_prime * width
+            return a + (1 - s) * (out - n0 + self.x_max_val + diff(n0, x0) * width)
+        n0, x0, n1, x1 = extra   # :878-882
+        a = -0.5 * (1 - s) ** 2 * width * self.x_min_prime + 0.5 * s ** 2 * width * self.x_max_prime
+        return a + 0.5 * s ** 2 * (out - n1 - 0.5 * diff(n1, x1) * width) \
+            + 0.5 * (1 - s) ** 2 * (out - n0 + 0.5 * diff(n0, x0) * width)
 
 
 class DirichletBVPSpherical(_Condition):  # :887-956
@@ -206,7 +293,8 @@ class DirichletBVPSpherical(_Condition):  # :887-956
 NAMESPACE = types.SimpleNamespace(
     diff=diff, grad=grad, div=div, curl=curl, laplacian=laplacian, spherical_laplacian=spherical_laplacian,
     FCNN=FCNN, SinActv=SinActv, NoCondition=NoCondition, IVP=IVP, BundleIVP=BundleIVP,
-    DirichletBVP2D=DirichletBVP2D, IBVP1D=IBVP1D, DirichletBVPSpherical=DirichletBVPSpherical)
+    DirichletBVP2D=DirichletBVP2D, IBVP1D=IBVP1D, DoubleEndedBVP1D=DoubleEndedBVP1D,
+    DirichletBVPSpherical=DirichletBVPSpherical)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -3,7 +3,7 @@
 Run in the build container only (``python tests/golden/generate.py``); the GPU box has no /root/reference, so the
 ``.npz`` files written next to this script are committed and are what the tests read.
 
-For every BASELINE.json workload (workloads.py, C1..C5) at N points the script evaluates exactly the closure of
+For every workload of workloads.py (BASELINE.json's C1..C5 and the extension cases x1..) at N points the script evaluates exactly the closure of
 the reference (solvers.py:369-395): ``funcs = cond.enforce(net, *coords)``; ``r = cat(diff_eqs(*funcs, *coords))``;
 ``loss = (r**2).mean()``; ``loss.backward()`` -- in float64 (the reference's import default) on inputs whose
 values are float32-representable (so that the fp64 result is "the exact answer" for the fp32 inputs the CUDA path
@@ -27,19 +27,21 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import ref_shim  # noqa: E402
 import workloads  # noqa: E402
 
-GOLDEN_N = {"c1": 256, "c2": 256, "c3": 256, "c4": 256, "c5": 256}
+GOLDEN_N = {"c1": 256, "c2": 256, "c3": 256, "c4": 256, "c5": 256, "x1": 256, "x2": 256, "x3": 256, "x4": 256, "x5": 256,
+            "x6": 256}
 
 
 def reference_namespace():
     ref_shim.import_reference()
     from neurodiffeq import diff
     from neurodiffeq.networks import FCNN, SinActv
-    from neurodiffeq.conditions import IVP, BundleIVP, DirichletBVP2D, IBVP1D, DirichletBVPSpherical, NoCondition
+    from neurodiffeq.conditions import (IVP, BundleIVP, DirichletBVP2D, IBVP1D, DirichletBVPSpherical, NoCondition,
+                                        DoubleEndedBVP1D)
     from neurodiffeq.operators import spherical_laplacian, laplacian, grad, div, curl
     return types.SimpleNamespace(
         diff=diff, FCNN=FCNN, SinActv=SinActv, IVP=IVP, BundleIVP=BundleIVP, DirichletBVP2D=DirichletBVP2D,
         IBVP1D=IBVP1D, DirichletBVPSpherical=DirichletBVPSpherical, NoCondition=NoCondition,
-        spherical_laplacian=spherical_laplacian, laplacian=laplacian, grad=grad, div=div, curl=curl)
+        DoubleEndedBVP1D=DoubleEndedBVP1D, spherical_laplacian=spherical_laplacian, laplacian=laplacian, grad=grad, div=div, curl=curl)
 
 
 def distinct(nets):
@@ -70,7 +72,10 @@ def run_closure(wl, nets, conds, coords_np, dtype):
 
 def main():
     nd = reference_namespace()
-    for key in workloads.NAMES:
+    only = sys.argv[1:]   # e.g. `generate.py x1 x2`: (re)generate just these; default: every workload
+    for key in workloads.NAMES + workloads.EXTRA_NAMES:
+        if only and key not in only:
+            continue
         wl = workloads.build(nd, key)
         n_pts = GOLDEN_N[key]
         torch.manual_seed(0)

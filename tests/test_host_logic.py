@@ -5,6 +5,8 @@ import numpy as np
 import pytest
 import torch
 
+import workloads
+
 from neurodiffeq_b200 import generators as G
 from neurodiffeq_b200 import symbolic as S
 
@@ -116,8 +118,46 @@ def test_unsupported_features_raise_loudly():
     import torch.nn as nn
     with pytest.raises(NotImplementedError):   # activation without a jet rule
         TracedProblem([FCNN(1, 1, actv=nn.ReLU)], [NoCondition()], lambda u, t: [diff(u, t)], 1)
-    with pytest.raises(NotImplementedError):   # Neumann IBVP evaluates the net at boundary points
-        IBVP1D(0, 1, 0, lambda x: x, x_min_prime=lambda t: 0, x_max_val=lambda t: 0).enforce(
-            FCNN(2, 1), S.Graph().coord(0), S.Graph().coord(1))
+    # Neumann IBVP evaluates the net at a boundary abscissa: one constant coordinate + a second instance of the module
+    heat = lambda u, x, t: [diff(u, t) - diff(u, x, order=2)]  # noqa: E731
+    net = FCNN(2, 1)
+    tp = TracedProblem([net], [IBVP1D(0, 1, 0, lambda x: x, x_min_prime=lambda t: 0, x_max_val=lambda t: 0)], heat, 2)
+    assert tp.const_coords == (0.0,) and tp.n_coords == 3 and [nd.in_coord for nd in tp.nets] == [(0, 1), (2, 1)]
+    assert tp.nets[0].module is tp.nets[1].module
+    with pytest.raises(NotImplementedError):   # Neumann data on both ends of a PDE: 6 jet directions, the kernels carry 4
+        from neurodiffeq_b200.engine import pad_scheme
+        TracedProblem([net], [IBVP1D(0, 1, 0, lambda x: x, x_min_prime=lambda t: 0, x_max_prime=lambda t: 0)], heat, 2,
+                      pad_scheme=pad_scheme)
+    with pytest.raises(RuntimeError):          # a boundary leaf outside a trace has no meaning
+        S.Graph().const_coord(1.0)
     with pytest.raises(NotImplementedError):   # torch.cat of traced columns outside enforce()
         TracedProblem([FCNN(1, 1)], [NoCondition()], lambda u, t: [torch.cat([u, t], 1)], 1)
+
+
+@pytest.mark.parametrize("key", workloads.NAMES + workloads.EXTRA_NAMES)
+def test_conditions_and_diff_on_eager_tensors_equal_the_oracle(key):
+    """Outside the solver the product's conditions / diff / operators are ordinary torch code with the reference's
+    semantics (conditions.py:41-57 and the parameterize of each class): same u and residual as the oracle, incl. the
+    Neumann branches that evaluate the network at a boundary leaf."""
+    from helpers import product_namespace, get_params
+    from oracle import reference_port as oracle
+    wl = workloads.build(product_namespace(), key)
+    torch.manual_seed(1)
+    nets, conds = wl.make_nets(), wl.make_conditions()
+    for m in nets:
+        m.double()
+    owl = workloads.build(oracle.NAMESPACE, key)
+    onets, oconds = owl.make_nets(), owl.make_conditions()
+    oracle.load_params(onets, get_params(nets), dtype=torch.float64)
+    coords_np = workloads.sample_coords(wl, 64, seed=3)
+
+    def run(nets_, conds_, w):
+        cols = [torch.as_tensor(c, dtype=torch.float64).reshape(-1, 1).requires_grad_(True) for c in coords_np]
+        funcs = [c.enforce(n, *cols) for n, c in zip(nets_, conds_)]
+        res = workloads.bundle_eq_wrapper(w)(*funcs, *cols)
+        return [f.detach().numpy() for f in funcs], [r.detach().numpy() for r in res]
+
+    fu, fr = run(nets, conds, wl)
+    gu, gr = run(onets, oconds, owl)
+    for a, b in zip(fu + fr, gu + gr):
+        np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-12)

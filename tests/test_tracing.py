@@ -1,7 +1,5 @@
 """Host logic: tracing the reference-style problem definitions -> programs; algebra of the kernels (numpy mirror)
 against golden vectors produced by the unmodified reference."""
-import types
-
 import numpy as np
 import pytest
 import torch
@@ -11,16 +9,17 @@ from conftest import load_golden
 from oracle import jet_numpy
 
 
-def product_namespace():
-    from neurodiffeq_b200 import diff
-    from neurodiffeq_b200 import operators as ops
-    from neurodiffeq_b200.networks import FCNN, SinActv
-    from neurodiffeq_b200 import conditions as c
-    return types.SimpleNamespace(
-        diff=diff, FCNN=FCNN, SinActv=SinActv, IVP=c.IVP, BundleIVP=c.BundleIVP, DirichletBVP2D=c.DirichletBVP2D,
-        IBVP1D=c.IBVP1D, DirichletBVPSpherical=c.DirichletBVPSpherical, NoCondition=c.NoCondition,
-        spherical_laplacian=ops.spherical_laplacian, laplacian=ops.laplacian, grad=ops.grad, div=ops.div,
-        curl=ops.curl)
+from helpers import product_namespace  # noqa: E402
+
+
+def params_per_instance(tp, flat_params):
+    """golden params are in state_dict order over the distinct modules; instances of one module share them"""
+    by_module, it, per_net = {}, iter(flat_params), []
+    for nd in tp.nets:
+        if id(nd.module) not in by_module:
+            by_module[id(nd.module)] = [next(it) for _ in range(2 * len(nd.linears))]
+        per_net.append(by_module[id(nd.module)])
+    return per_net
 
 
 def trace(key):
@@ -31,19 +30,17 @@ def trace(key):
     return wl, nets, conds, tp
 
 
-EXPECTED_CHANNELS = {"c1": (1, 0), "c2": (2, 2), "c3": (2, 1), "c4": (3, 3), "c5": (1, 0)}
+EXPECTED_CHANNELS = {"c1": (1, 0), "c2": (2, 2), "c3": (2, 1), "c4": (3, 3), "c5": (1, 0),
+                     # Neumann ends: the network is also evaluated at a constant coordinate; heat: x, t, boundary, t+boundary
+                     "x1": (4, 4), "x2": (4, 4), "x3": (2, 1), "x4": (2, 1), "x5": (3, 1), "x6": (1, 1)}
 
 
-@pytest.mark.parametrize("key", workloads.NAMES)
+@pytest.mark.parametrize("key", workloads.NAMES + workloads.EXTRA_NAMES)
 def test_traced_problem_matches_reference_golden(key):
     wl, nets, conds, tp = trace(key)
     assert (tp.scheme.n1, tp.scheme.n2) == EXPECTED_CHANNELS[key]
     gold = load_golden(wl.name)
-    # golden params are in state_dict order over the distinct nets = [W0,b0,W1,b1,...] per net
-    per_net, it = [], iter(gold["params"])
-    for nd in tp.nets:
-        per_net.append([next(it) for _ in range(2 * len(nd.linears))])
-    out = jet_numpy.run_traced(tp, per_net, gold["coords"])
+    out = jet_numpy.run_traced(tp, params_per_instance(tp, gold["params"]), gold["coords"])
     rms = np.sqrt((gold["residual"] ** 2).mean())
     np.testing.assert_allclose(out["u"], gold["u"], rtol=1e-10, atol=1e-12)
     assert np.abs(out["residual"] - gold["residual"]).max() <= 1e-9 * rms
@@ -55,7 +52,8 @@ def test_traced_problem_matches_reference_golden(key):
           "slots", tp.prog_train.n_slots)
 
 
-@pytest.mark.parametrize("key,wl,channels", [("c2", 2, 4), ("c4", 3, 5), ("c3", 0, 4), ("c5", 0, 2)])
+@pytest.mark.parametrize("key,wl,channels", [("c2", 2, 4), ("c4", 3, 5), ("c3", 0, 4), ("c5", 0, 2), ("x1", 4, 6),
+                                             ("x2", 4, 6), ("x5", 3, 5)])
 def test_combined_second_order_channel(key, wl, channels):
     """Residuals affine in the pure second derivatives with coordinate-only coefficients are carried as ONE weighted
     channel (forward-Laplacian style): C2 5 -> 4 channels, C4 7 -> 5; values and gradients are unchanged."""
@@ -63,13 +61,10 @@ def test_combined_second_order_channel(key, wl, channels):
     from neurodiffeq_b200.engine import pad_scheme
     wl_, nets, conds, _ = trace(key)
     tp = TracedProblem(nets, conds, workloads.bundle_eq_wrapper(wl_), len(wl_.coord_names), pad_scheme=pad_scheme,
-                       combine_seconds=lambda a, b: (a, b) in ((2, 2), (3, 3)))
+                       combine_seconds=lambda a, b: (a, b) in ((2, 2), (3, 3), (4, 4)))
     assert tp.wl == wl and tp.n_channels == channels
     gold = load_golden(wl_.name)
-    per_net, it = [], iter(gold["params"])
-    for nd in tp.nets:
-        per_net.append([next(it) for _ in range(2 * len(nd.linears))])
-    out = jet_numpy.run_traced(tp, per_net, gold["coords"])
+    out = jet_numpy.run_traced(tp, params_per_instance(tp, gold["params"]), gold["coords"])
     rms = np.sqrt((gold["residual"] ** 2).mean())
     assert np.abs(out["residual"] - gold["residual"]).max() <= 1e-9 * rms
     gn = np.sqrt(sum((g ** 2).sum() for g in gold["grads"]))

@@ -149,8 +149,56 @@ def _c5(nd):
                     _fcnn_flops((5, 64, 64, 2), 2), (0, 1))
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Extension workloads: conditions with Neumann data, which evaluate the network AT a boundary abscissa
+# (reference conditions.py:585-596, 823-834).  Not BASELINE configs -- parity cases for the widened condition family.
+# ----------------------------------------------------------------------------------------------------------------------
+def _heat(nd, name, neumann_side):
+    def make_nets():
+        return [nd.FCNN(n_input_units=2, n_output_units=1, hidden_units=(64, 64))]
+
+    def make_conditions():
+        kw = dict(x_min=0.0, x_max=1.0, t_min=0.0, t_min_val=lambda x: torch.sin(0.5 * np.pi * x))
+        if neumann_side == "right":   # Dirichlet at x0, Neumann at x1 (conditions.py:670-676)
+            kw.update(x_min_val=lambda t: 0.2 * torch.sin(t), x_max_prime=lambda t: 0.1 * t)
+        else:                         # Neumann at x0, Dirichlet at x1 (conditions.py:680-686)
+            kw.update(x_min_prime=lambda t: 0.1 * t, x_max_val=lambda t: 1.0 + 0.2 * torch.sin(t))
+        return [nd.IBVP1D(**kw)]
+
+    def diff_eqs(u, x, t):
+        return [nd.diff(u, t) - 0.3 * nd.diff(u, x, order=2)]
+
+    return Workload(name, "Solver2D", ("x", "t"), ((0.0, 1.0), (0.0, 1.0)), [((2, 64, 64, 1), "tanh")], make_nets,
+                    make_conditions, diff_eqs, 1, 16384, 2 * _fcnn_flops((2, 64, 64, 1), 9), None)
+
+
+def _bvp(nd, name, kw):
+    def make_nets():
+        return [nd.FCNN(n_input_units=1, n_output_units=1, hidden_units=(32, 32))]
+
+    def make_conditions():
+        return [nd.DoubleEndedBVP1D(0.0, 1.0, **kw)]
+
+    def diff_eqs(u, x):
+        return [nd.diff(u, x, order=2) + u - x]
+
+    n_inst = 1 + sum(k.endswith("prime") for k in kw)
+    return Workload(name, "Solver1D", ("x",), ((0.0, 1.0),), [((1, 32, 32, 1), "tanh")], make_nets, make_conditions,
+                    diff_eqs, 1, 4096, n_inst * _fcnn_flops((1, 32, 32, 1), 3), None)
+
+
+_EXTRA = {
+    "x1": lambda nd: _heat(nd, "x1_heat_dirichlet_neumann", "right"),
+    "x2": lambda nd: _heat(nd, "x2_heat_neumann_dirichlet", "left"),
+    "x3": lambda nd: _bvp(nd, "x3_bvp_dirichlet_neumann", dict(x_min_val=1.0, x_max_prime=0.5)),
+    "x4": lambda nd: _bvp(nd, "x4_bvp_neumann_dirichlet", dict(x_min_prime=-0.5, x_max_val=0.25)),
+    "x5": lambda nd: _bvp(nd, "x5_bvp_neumann_neumann", dict(x_min_prime=-0.5, x_max_prime=0.5)),
+    "x6": lambda nd: _bvp(nd, "x6_bvp_dirichlet_dirichlet", dict(x_min_val=1.0, x_max_val=0.25)),
+}
 _BUILDERS = {"c1": _c1, "c2": _c2, "c3": _c3, "c4": _c4, "c5": _c5}
-NAMES = tuple(_BUILDERS)
+NAMES = tuple(_BUILDERS)          # BASELINE.json configs
+EXTRA_NAMES = tuple(_EXTRA)       # widened condition family
+_BUILDERS.update(_EXTRA)
 
 
 def build(nd, key):
