@@ -25,6 +25,7 @@ import torch.nn as nn
 
 from .conditions import BaseCondition
 from .engine import FusedProblem
+from .losses import _losses, h1_rows
 from .generators import Generator1D, Generator2D, GeneratorSpherical, SamplerGenerator
 from .networks import FCNN
 from .parallel import shard_bounds
@@ -127,8 +128,11 @@ class BaseSolver:
         if n_coords is None:
             n_coords = len(self.generator["train"].get_examples())
         self.n_coords = n_coords
-        self.problem = FusedProblem(self.nets, self.conditions, self._traced_diff_eqs, n_coords,
+        self._set_loss_fn(loss_fn)      # before tracing: the 'h1' loss adds derivative rows to the traced residuals
+        self.problem = FusedProblem(self.nets, self.conditions,
+                                    self._h1_rows if self._h1 else self._traced_diff_eqs, n_coords,
                                     coords_for_condition=self._coords_for_condition, device=device)
+        self.n_eq = self.problem.n_eq - (n_coords if self._h1 else 0)     # the user's equations
         self.device = self.problem.device
 
         self.optimizer = optimizer if optimizer else torch.optim.Adam(
@@ -136,7 +140,6 @@ class BaseSolver:
         if _requires_closure(self.optimizer):
             raise NotImplementedError("closure-based optimizers (LBFGS, reference solvers.py:398-400) are not "
                                       "supported by the fused solvers yet")
-        self._set_loss_fn(loss_fn)
         self.best_nets_theta = None
         self.lowest_loss = None
         self.local_epoch = 0
@@ -155,6 +158,11 @@ class BaseSolver:
     def _coords_for_condition(self, k, cond, coords):
         return tuple(coords)
 
+    def _h1_rows(self, *variables):
+        """Residual rows of the 'h1' loss (reference losses.py:17-20): the equations, then d(sum of equations)/d(coord) for
+        every coordinate of the batch -- the mean of the squares of all of them is the loss."""
+        return h1_rows(self._traced_diff_eqs, self.n_funcs)(*variables)
+
     def additional_loss(self, residual, funcs, coords):
         return 0.0
 
@@ -163,6 +171,7 @@ class BaseSolver:
         # Any other callable (residual, funcs, coords) -> scalar is differentiated by autograd w.r.t. the residual
         # only; dL/dr is then handed to the kernels (funcs / coords are passed detached).
         self._custom_loss = None
+        self._h1 = False
         if criterion is None or (isinstance(criterion, str) and criterion.lower() == "l2") \
                 or isinstance(criterion, nn.MSELoss):
             self.loss_fn = lambda r, f, x: (r ** 2).mean()
@@ -170,8 +179,16 @@ class BaseSolver:
             self.loss_fn = lambda r, f, x: criterion(r, torch.zeros_like(r))
             self._custom_loss = self.loss_fn
         elif isinstance(criterion, str):
-            raise NotImplementedError(f"loss '{criterion}' of neurodiffeq.losses is not available in the fused solvers "
-                                      f"(implemented: 'l2'); pass a callable (residual, funcs, coords) -> scalar")
+            name = criterion.lower()
+            if name not in _losses:
+                raise KeyError(criterion)                     # the reference's `_losses[criterion.lower()]`
+            self.loss_fn = _losses[name]
+            if name == "h1":      # fused: mean square over [equations | d(sum of equations)/d(coords)], see _h1_rows
+                self._h1 = True
+            elif name == "h1 semi":
+                raise NotImplementedError("loss 'h1 semi' is not available in the fused solvers (see losses.py)")
+            else:                 # 'l1', 'infinity': autograd on the residual matrix -> dL/dr -> kernels
+                self._custom_loss = self.loss_fn
         elif callable(criterion):
             self.loss_fn = criterion
             self._custom_loss = criterion
@@ -361,7 +378,7 @@ class BaseSolver:
             fp.pack()
         else:
             _, r, _ = fp.forward([c.reshape(-1) for c in coords], want_u=False, want_residual=True)
-        rs = [r[e].reshape(-1, 1) if no_reshape else r[e].reshape(shape) for e in range(r.shape[0])]
+        rs = [r[e].reshape(-1, 1) if no_reshape else r[e].reshape(shape) for e in range(self.n_eq)]
         if to_numpy:
             rs = [x.detach().cpu().numpy() for x in rs]
         return rs if len(rs) > 1 else rs[0]

@@ -109,7 +109,7 @@ def backward(weights, act, x_in, dirs_in, n2, z_store, ybar, wl=None):
     return gW, gb
 
 
-def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True):
+def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True, rbar=None):
     """Evaluate a TracedProblem end to end in float64.
 
     ``params_per_net``: list (per network INSTANCE of ``tp.nets``; instances of one module get the same arrays) of
@@ -138,12 +138,16 @@ def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True):
             for c in range(C):
                 y_rows[tp.yrow0[k] + o * C + c] = y[c, o]
     u, r, _ = S.evaluate_program(tp.prog_eval, coords, y_rows, n_u=tp.n_funcs, n_r=tp.n_eq)
-    out = dict(u=u, residual=r, loss=float((r ** 2).mean()), y=y_rows)
+    out = dict(u=u, residual=r, loss=float((r ** 2).mean()) if r.size else 0.0, y=y_rows)
     if want_grad:
         n_glob = N if n_global is None else n_global
         scale = 2.0 / (n_glob * tp.n_eq)
-        _, r2, seeds = S.evaluate_program(tp.prog_train, coords, y_rows, params=[scale], n_r=tp.n_eq,
-                                          n_seed=tp.n_yrows)
+        if rbar is None:   # L = mean(r^2) over the global batch
+            _, r2, seeds = S.evaluate_program(tp.prog_train, coords, y_rows, params=[scale], n_r=tp.n_eq,
+                                              n_seed=tp.n_yrows)
+        else:              # externally supplied dL/dr [n_eq, N] (custom loss functions)
+            _, r2, seeds = S.evaluate_program(tp.prog_train_ext, coords, y_rows, rbar=np.asarray(rbar, dtype=np.float64),
+                                              params=[scale], n_r=tp.n_eq, n_seed=tp.n_yrows)
         assert np.allclose(r2, r)
         by_module = {}   # instances that share a module (network evaluated at a boundary too) add up, like autograd
         for k, nd in enumerate(tp.nets):

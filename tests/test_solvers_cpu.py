@@ -1,0 +1,74 @@
+"""Host logic of the fused solvers on the CPU: the engine is replaced by a float64 stand-in built on the numpy mirror of
+the kernels (tests/cpu_engine.py), everything else -- tracing, epoch loop, named / custom losses, best-network tracking,
+solutions and residuals -- is the product's code.  Training must follow the oracle (autograd + torch Adam, float64) to
+rounding level.  The GPU suite repeats these through the real kernels at fp32 tolerances."""
+import numpy as np
+import pytest
+import torch
+
+import workloads
+from cpu_engine import CpuFusedProblem
+from helpers import get_params
+from test_solvers_gpu import make_solver, oracle_training
+from test_losses_gpu import oracle_training_with_loss
+
+
+@pytest.fixture(autouse=True)
+def cpu_engine(monkeypatch):
+    import neurodiffeq_b200.solvers as S
+    monkeypatch.setattr(S, "FusedProblem", CpuFusedProblem)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)
+
+
+@pytest.mark.parametrize("key", ["c1", "c2", "c4", "c5", "x1", "x4", "x5"])
+def test_fit_tracks_oracle_adam_cpu(key):
+    n, epochs = 160, 4
+    wl, solver, nets, coords_np = make_solver(key, n)
+    params0 = get_params(nets)
+    solver.fit(epochs, tqdm_file=None)
+    ref_losses, ref_params = oracle_training(key, params0, coords_np, epochs)
+    np.testing.assert_allclose(solver.metrics_history["train_loss"], ref_losses, rtol=5e-7)
+    np.testing.assert_allclose(solver.metrics_history["valid_loss"][:-1], ref_losses[1:], rtol=5e-7)
+    for a, b in zip(get_params(nets), ref_params):
+        np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-11)
+    assert solver.global_epoch == epochs and solver.lowest_loss == min(solver.metrics_history["valid_loss"])
+
+
+@pytest.mark.parametrize("loss_name", ["l1", "infinity", "h1"])
+def test_named_losses_cpu(loss_name):
+    key, n, epochs = "c1", 120, 4
+    wl, solver, nets, coords_np = make_solver(key, n, loss_fn=loss_name)
+    params0 = get_params(nets)
+    solver.fit(epochs, tqdm_file=None)
+    ref_losses, ref_params = oracle_training_with_loss(key, params0, coords_np, epochs, loss_name)
+    np.testing.assert_allclose(solver.metrics_history["train_loss"], ref_losses, rtol=5e-7)
+    for a, b in zip(get_params(nets), ref_params):
+        np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-11)
+    r = solver.get_residuals(torch.linspace(0.5, 2.0, 7), best=False)
+    assert isinstance(r, list) and len(r) == wl.n_eq and r[0].shape == (7,)
+
+
+def test_loss_name_errors_cpu():
+    with pytest.raises(KeyError):
+        make_solver("c1", 16, loss_fn="l3")
+    with pytest.raises(NotImplementedError):
+        make_solver("c1", 16, loss_fn="h1 semi")
+
+
+def test_custom_loss_callable_and_solution_cpu():
+    def weighted(residual, funcs, coords):          # (residual, funcs, coords) -> scalar, reference solvers.py:66-79
+        return (residual ** 2 * (1.0 + coords[0] ** 2)).mean()
+
+    wl, solver, nets, coords_np = make_solver("x3", 100, loss_fn=weighted)
+    l0 = None
+    solver.fit(3, tqdm_file=None)
+    hist = solver.metrics_history["train_loss"]
+    assert len(hist) == 3 and all(np.isfinite(hist))
+    sol = solver.get_solution(best=False)
+    x = torch.tensor([0.0, 0.5, 1.0])
+    u = sol(x, to_numpy=True)
+    assert u.shape == (3,) and abs(u[0] - 1.0) < 1e-12     # Dirichlet end of x3: u(0) = 1 for any weights
+    del l0

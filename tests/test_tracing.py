@@ -131,3 +131,41 @@ def test_unused_coordinate_gives_zero_and_order3_raises():
         TracedProblem([net], [NoCondition()], lambda u, t: [diff(u, t, order=3)], 1)
     with pytest.raises(TypeError):
         TracedProblem([net], [NoCondition()], lambda u, t: [u if u > 0 else -u], 1)
+
+
+@pytest.mark.parametrize("key", ["c1", "c5"])
+def test_h1_loss_is_the_mean_square_of_augmented_rows(key):
+    """'h1' (reference losses.py:17-20) = mean square of [residual | grad(residual, *coords)], where grad differentiates
+    the SUM of the residual columns: traced as extra residual rows, it is the plain fused L2 path.  Checked against
+    autograd (oracle) for loss and parameter gradients on a first-order system (second-order jets suffice)."""
+    from neurodiffeq_b200.tracing import TracedProblem
+    from neurodiffeq_b200.losses import h1_rows, _losses
+    from oracle import reference_port as oracle
+    wl = workloads.build(product_namespace(), key)
+    torch.manual_seed(4)
+    nets, conds = wl.make_nets(), wl.make_conditions()
+    n_funcs = len(conds)
+    tp = TracedProblem(nets, conds, h1_rows(workloads.bundle_eq_wrapper(wl), n_funcs), len(wl.coord_names))
+    assert tp.n_eq == wl.n_eq + len(wl.coord_names)
+    from helpers import get_params
+    params = get_params(nets)
+    coords = workloads.sample_coords(wl, 200, seed=8)
+    out = jet_numpy.run_traced(tp, params_per_instance(tp, params), coords)
+    # autograd: the reference's loss function on the oracle's residual matrix
+    owl = workloads.build(oracle.NAMESPACE, key)
+    onets, oconds = owl.make_nets(), owl.make_conditions()
+    oracle.load_params(onets, params, dtype=torch.float64)
+    cols = [torch.as_tensor(c, dtype=torch.float64).reshape(-1, 1).requires_grad_(True) for c in coords]
+    funcs = [c.enforce(n, *cols) for n, c in zip(onets, oconds)]
+    res = torch.cat(workloads.bundle_eq_wrapper(owl)(*funcs, *cols), dim=1)
+    g = oracle.grad(res, *cols)
+    loss = (torch.cat([res, *g], dim=1) ** 2).mean()
+    loss_product_eager = float(_losses["h1"](res, funcs, cols).detach())   # the product's own loss function on tensors
+    loss.backward()
+    loss = float(loss.detach())
+    assert abs(loss_product_eager - loss) <= 1e-12 * loss
+    assert abs(out["loss"] - loss) <= 1e-10 * loss
+    ref_grads = [p.grad.numpy() for m in oracle.distinct_modules(onets) for p in m.parameters()]
+    gn = np.sqrt(sum((a ** 2).sum() for a in ref_grads))
+    dn = np.sqrt(sum(((a - b.reshape(a.shape)) ** 2).sum() for a, b in zip(ref_grads, out["grads"])))
+    assert dn <= 1e-9 * gn
