@@ -4,7 +4,8 @@ host" (BASELINE.json north_star).
 The fused solvers only need ``generator.get_examples()`` (tensors of ``size`` points per coordinate) and
 ``generator.size`` (reference solvers.py:49-52), so any reference generator object works as well.  This module re-states
 the commonly used ones so that user code runs with an import-root change only: 1-D / 2-D / 3-D / spherical samplers
-and the ``+`` (concat), ``*`` (ensemble) and ``^`` (mesh) combinators.  Samples are float32 CPU tensors WITHOUT
+the N-D tensor-product sampler, the ``+`` (concat), ``*`` (ensemble) and ``^`` (mesh) combinators and the
+wrappers (static, predefined, transform, filter, resample, batch).  Samples are float32 CPU tensors WITHOUT
 ``requires_grad``: the fused path never builds an autograd graph over coordinates.
 
 Sampling laws follow the reference: noisy grids add N(0, (step/4)^2) noise (generators.py:149-158, 253-266), spherical
@@ -259,6 +260,144 @@ class PredefinedGenerator(BaseGenerator):
 
     def get_examples(self):
         return self.xs[0] if len(self.xs) == 1 else tuple(self.xs)
+
+
+class TransformGenerator(BaseGenerator):
+    """Applies per-coordinate maps (``transforms``: a list, ``None`` entries = identity) or one joint map (``transform``:
+    ``f(*xs) -> tuple``) to another generator's samples (generators.py:758-801)."""
+
+    def __init__(self, generator, transforms=None, transform=None):
+        super().__init__()
+        if transforms is not None and transform is not None:
+            raise ValueError("transform and transforms cannot be both specified")
+        self.generator, self.size = generator, generator.size
+        self._per_axis = None if transforms is None else [t if t is not None else (lambda x: x) for t in transforms]
+        self._joint = transform
+
+    def get_examples(self):
+        xs = self.generator.get_examples()
+        single = isinstance(xs, torch.Tensor)
+        if self._per_axis is not None:
+            return self._per_axis[0](xs) if single else tuple(t(x) for t, x in zip(self._per_axis, xs))
+        if self._joint is not None:
+            return self._joint(xs) if single else self._joint(*xs)
+        return xs
+
+
+class FilterGenerator(BaseGenerator):
+    """Keeps the samples where ``filter_fn(list_of_tensors)`` (a boolean mask) is true (generators.py:904-953);
+    ``size`` follows the number of survivors unless ``update_size=False``."""
+
+    def __init__(self, generator, filter_fn, size=None, update_size=True):
+        super().__init__()
+        self.generator, self.filter_fn, self.update_size = generator, filter_fn, update_size
+        self.size = generator.size if size is None else size
+
+    def get_examples(self):
+        xs = list(_as_tuple(self.generator.get_examples()))
+        keep = self.filter_fn(xs)
+        xs = [x[keep] for x in xs]
+        if self.update_size:
+            self.size = len(xs[0])
+        return xs[0] if len(xs) == 1 else xs
+
+
+class ResampleGenerator(BaseGenerator):
+    """A random subset (``replacement=False``: a permutation prefix) or bootstrap sample (``True``) of ``size`` points
+    of another generator's batch; the same rows are taken from every coordinate (generators.py:956-993)."""
+
+    def __init__(self, generator, size=None, replacement=False):
+        super().__init__()
+        self.generator, self.replacement = generator, replacement
+        self.size = generator.size if size is None else size
+
+    def get_examples(self):
+        m = self.generator.size
+        rows = torch.randint(m, (self.size,)) if self.replacement else torch.randperm(m)[:self.size]
+        xs = self.generator.get_examples()
+        return xs[rows] if isinstance(xs, torch.Tensor) else [x[rows] for x in xs]
+
+
+class BatchGenerator(BaseGenerator):
+    """Serves another generator's samples ``batch_size`` at a time from a cache that is refilled when it runs short
+    (generators.py:996-1043)."""
+
+    def __init__(self, generator, batch_size):
+        super().__init__()
+        if generator.size <= 0:
+            raise ValueError(f"generator has size {generator.size} <= 0")
+        self.generator, self.size = generator, batch_size
+        self._cache = list(_as_tuple(generator.get_examples()))
+
+    def get_examples(self):
+        while len(self._cache[0]) < self.size:
+            more = _as_tuple(self.generator.get_examples())
+            self._cache = [torch.cat([old, new]) for old, new in zip(self._cache, more)]
+        batch = [x[:self.size] for x in self._cache]
+        self._cache = [x[self.size:] for x in self._cache]
+        return batch[0] if len(batch) == 1 else batch
+
+
+class GeneratorND(BaseGenerator):
+    """Tensor-product points in N dimensions with a sampling law per axis (generators.py:419-570): 'equally-spaced',
+    'uniform' (drawn once), 'log-spaced', 'exp-spaced' (equally spaced in ``base**x``), 'chebyshev'/'chebyshev1',
+    'chebyshev2'; optional ``cut=(lo, hi)`` slices per axis; with ``noisy`` every call adds N(0, std^2) noise to the mesh
+    (std per axis: ``r_noise_std`` or a quarter grid step, scaled by the node for the log / exp laws, 0 for 'uniform');
+    ``abs_value`` folds the noisy points to non-negative values."""
+
+    def __init__(self, grid=(10, 10), r_min=(0.0, 0.0), r_max=(1.0, 1.0), methods=("equally-spaced", "equally-spaced"),
+                 noisy=True, r_noise_std=None, **kwargs):
+        super().__init__()
+        self.grid, self.r_min, self.r_max, self.methods = grid, r_min, r_max, methods
+        self.noisy, self.r_noise_std = noisy, r_noise_std
+        seq = lambda v: (v,) if isinstance(v, (int, float, str)) else tuple(v)  # noqa: E731
+        grid, lo, hi, methods = seq(grid), seq(r_min), seq(r_max), seq(methods)
+        stds = None if not r_noise_std else seq(r_noise_std)
+        n_axes = len(grid)
+        self.size = int(np.prod(grid))
+        cut = kwargs.pop("cut", tuple((None, None) for _ in range(n_axes)))
+        base = kwargs.pop("base", tuple(10 for _ in range(n_axes)))
+        abs_value = kwargs.pop("abs_value", False)
+        if kwargs:
+            raise ValueError(f"Unknown keyword argument(s): {list(kwargs.keys())}")
+        base = seq(base)
+        if cut[0] is None or isinstance(cut[0], (int, float)):
+            cut = (cut,)
+        nodes, sigmas = [], []
+        for d in range(n_axes):
+            a, b, n, law = lo[d], hi[d], grid[d], methods[d]
+            sd = stds[d] if stds else ((b - a) / n) / 4.0
+            if law == "equally-spaced":
+                x = torch.linspace(a, b, n, dtype=_F)
+                sg = torch.full((n,), sd, dtype=_F)
+            elif law == "uniform":
+                x = torch.rand(n) * (b - a) + a
+                sg = torch.zeros(n, dtype=_F)
+            elif law == "log-spaced":
+                x = torch.logspace(math.log10(a), math.log10(b), n, dtype=_F)
+                sg = sd * x
+            elif law == "exp-spaced":
+                x = torch.log(torch.linspace(base[d] ** a, base[d] ** b, n, dtype=_F)) / math.log(base[d])
+                sg = sd * x
+            elif law in ("chebyshev", "chebyshev1"):
+                x = _cheb1(a, b, n)
+                sg = torch.full((n,), sd, dtype=_F)
+            elif law == "chebyshev2":
+                x = _cheb2(a, b, n)
+                sg = torch.full((n,), sd, dtype=_F)
+            else:
+                raise ValueError(f"Unknown method: {law}")
+            nodes.append(x[cut[d][0]:cut[d][1]])
+            sigmas.append(sg[cut[d][0]:cut[d][1]])
+        self._mesh = [m.flatten() for m in torch.meshgrid(*nodes, indexing="ij")]
+        self._std = [m.flatten() for m in torch.meshgrid(*sigmas, indexing="ij")]
+        self._fold = abs_value
+
+    def get_examples(self):
+        if not self.noisy:
+            return tuple(self._mesh)
+        pts = tuple(torch.normal(m, s) for m, s in zip(self._mesh, self._std))
+        return tuple(p.abs() for p in pts) if self._fold else pts
 
 
 class SamplerGenerator(BaseGenerator):

@@ -161,3 +161,41 @@ def test_conditions_and_diff_on_eager_tensors_equal_the_oracle(key):
     gu, gr = run(onets, oconds, owl)
     for a, b in zip(fu + fr, gu + gr):
         np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-12)
+
+
+def test_wrapping_generators():
+    """TransformGenerator / FilterGenerator / ResampleGenerator / BatchGenerator / GeneratorND
+    (reference generators.py:419-570, 758-801, 904-1043)."""
+    base = G.Generator1D(64, 0.0, 1.0, "equally-spaced") * G.Generator1D(64, 2.0, 3.0, "equally-spaced")
+    x, y = G.TransformGenerator(base, transforms=[lambda a: 2 * a, None]).get_examples()
+    assert torch.allclose(x, 2 * torch.linspace(0, 1, 64)) and torch.allclose(y, torch.linspace(2, 3, 64))
+    s, d = G.TransformGenerator(base, transform=lambda a, b: (a + b, a - b)).get_examples()
+    assert torch.allclose(s - d, 2 * torch.linspace(2, 3, 64))
+    with pytest.raises(ValueError):
+        G.TransformGenerator(base, transforms=[None, None], transform=lambda a, b: (a, b))
+    f = G.FilterGenerator(base, lambda xs: xs[0] > 0.5)
+    fx, fy = f.get_examples()
+    assert f.size == len(fx) == len(fy) == 32 and fx.min() > 0.5
+    r = G.ResampleGenerator(base, size=10)
+    rx, ry = r.get_examples()
+    assert len(rx) == 10 and torch.allclose(ry - rx, torch.full((10,), 2.0)) and len(set(rx.tolist())) == 10
+    rb = G.ResampleGenerator(G.Generator1D(8, 0, 1, "equally-spaced"), size=50, replacement=True).get_examples()
+    assert rb.shape == (50,)
+    b = G.BatchGenerator(G.Generator1D(10, 0.0, 1.0, "equally-spaced"), 4)
+    got = torch.cat([b.get_examples() for _ in range(5)])       # 20 samples = two passes over the 10 cached nodes
+    assert b.size == 4 and torch.allclose(got, torch.linspace(0, 1, 10).repeat(2))
+    with pytest.raises(ValueError):
+        G.BatchGenerator(G.FilterGenerator(base, lambda xs: xs[0] > 2, size=0, update_size=False), 4)
+    nd = G.GeneratorND(grid=(4, 5, 3), r_min=(0.0, 1.0, 0.0), r_max=(1.0, 100.0, 2.0),
+                       methods=["equally-spaced", "log-spaced", "exp-spaced"], noisy=False)
+    a, bb, c = nd.get_examples()
+    assert nd.size == 60 and a.shape == bb.shape == c.shape == (60,)
+    assert torch.allclose(bb.reshape(4, 5, 3)[0, :, 0], torch.logspace(0, 2, 5))
+    assert torch.allclose(10 ** c.reshape(4, 5, 3)[0, 0], torch.linspace(1.0, 100.0, 3), rtol=1e-5)
+    noisy = G.GeneratorND(grid=(16,), r_min=0.0, r_max=1.0, methods="chebyshev2", noisy=True, abs_value=True, cut=(2, -2))
+    pts, = noisy.get_examples()
+    assert pts.shape == (12,) and (pts >= 0).all()
+    with pytest.raises(ValueError):
+        G.GeneratorND(grid=(4,), r_min=0.0, r_max=1.0, methods="sobol")
+    with pytest.raises(ValueError):
+        G.GeneratorND(grid=(4,), r_min=0.0, r_max=1.0, methods="uniform", stride=2)
