@@ -2,6 +2,10 @@
 // PJ_N1 = PJ_N2 = -1 builds the scheme-independent helpers (K2b reduce, loss finalize).
 #include "pinnjet_k2.cuh"
 #include "pinnjet_k1tc2.cuh"
+#ifdef PJ_EXPERIMENTAL
+#include <cstdlib>
+#include "pinnjet_k2tc.cuh"   // work in progress: only in libpinnjet_exp.so (build.py --experimental)
+#endif
 
 #ifndef PJ_WL
 #define PJ_WL 0
@@ -93,6 +97,23 @@ cudaError_t PJ_NAME(launch_k1_, PJ_N1, PJ_N2)(const K1Args& a, int grid, int sme
 }
 
 cudaError_t PJ_NAME(launch_k2_, PJ_N1, PJ_N2)(const K2Args& a, int grid, int smem, cudaStream_t s) {
+#ifdef PJ_EXPERIMENTAL
+    if constexpr (kC == 2 || kC == 4) {   // tensor-core reverse kernel, opt-in: PINNJET_TC_BWD=1
+        static int use_tc = -1;
+        if (use_tc < 0) {
+            const char* e = getenv("PINNJET_TC_BWD");
+            use_tc = (e && e[0] == '1') ? 1 : 0;
+        }
+        const K2tcLayout lay = k2tc_layout(a.spec, a.plan);
+        if (use_tc && lay.ok) {
+            static int ctc = 0;
+            auto kern = k2tc_backward_kernel<PJ_N1, PJ_N2, PJ_WL>;
+            if (cudaError_t e = configure(kern, ctc)) return e;
+            kern<<<grid, K2T_NCW * 32, lay.bytes, s>>>(a);
+            return cudaGetLastError();
+        }
+    }
+#endif
     static int c128 = 0, c256 = 0;
     if (a.plan.ntc == 128) {
         auto kern = k2_backward_kernel<128, kMinB2_128, kP, kQ, PJ_N1, PJ_N2, PJ_WL>;
