@@ -70,6 +70,43 @@ class NoCondition(BaseCondition):
         return output_tensor
 
 
+class EnsembleCondition(BaseCondition):
+    """Sub-condition i re-parameterises output unit i of ONE multi-output network; the function is the (N, k) block of
+    the k columns (reference conditions.py:157-202).  Traced: the block is a :class:`symbolic.SymColumns`, every column a
+    jet leaf of the same network, so ``u[:, i:i+1]`` in the user's equations is an ordinary traced function."""
+
+    def __init__(self, *sub_conditions, force=False):
+        super().__init__()
+        for i, c in enumerate(sub_conditions):
+            if c.__class__.enforce != BaseCondition.enforce:
+                msg = f"{c.__class__.__name__} (index={i})'s overrides BaseCondition's `.enforce` method. " \
+                      f"Ensembl'ing is likely not going to work."
+                if force:
+                    warnings.warn(msg)
+                else:
+                    raise ValueError(msg + "\nTry with `force=True` if you know what you are doing.")
+        self.conditions = sub_conditions
+
+    def enforce(self, net, *coordinates):
+        if not _sym.is_symbolic(*coordinates):
+            return self.parameterize(net(torch.cat(coordinates, dim=1)), *coordinates)
+        g = coordinates[0].g
+        in_coord = []
+        for c in coordinates:
+            if not isinstance(c, _sym.Sym) or c.op != "coord":
+                raise NotImplementedError("fused enforce(): the network inputs must be the sampled coordinates")
+            in_coord.append(c.imm)
+        n = g.register_net(net, in_coord)
+        return _sym.SymColumns([con.parameterize(g.net(n, i), *coordinates) for i, con in enumerate(self.conditions)])
+
+    def parameterize(self, output_tensor, *input_tensors):
+        if output_tensor.shape[1] != len(self.conditions):
+            raise ValueError(f"number of output units ({output_tensor.shape[1]}) "
+                             f"differs from number of conditions ({len(self.conditions)})")
+        return torch.cat([con.parameterize(output_tensor[:, i].view(-1, 1), *input_tensors)
+                          for i, con in enumerate(self.conditions)], dim=1)
+
+
 class _BundleConditionMixin:
     """Bundle parameters are taken per point from ``thetas`` by index (reference conditions.py:78-135)."""
 

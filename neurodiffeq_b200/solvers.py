@@ -36,6 +36,19 @@ def _requires_closure(optimizer):
     return isinstance(optimizer, torch.optim.LBFGS)
 
 
+def _functions(tp, u, shape=None):
+    """Rows of the kernel's ``u`` [n_rows, N] -> one tensor per condition: an (N, 1) column (or ``shape``-shaped values),
+    or the (N, k) block of an EnsembleCondition (reference conditions.py:197-202)."""
+    out = []
+    for rows in tp.func_rows:
+        if len(rows) == 1:
+            out.append(u[rows[0]].reshape(-1, 1) if shape is None else u[rows[0]].reshape(shape))
+        else:
+            block = torch.stack([u[r] for r in rows], dim=1)
+            out.append(block if shape is None else block.reshape(tuple(shape) + (len(rows),)))
+    return out
+
+
 def _unique(params):
     seen, out = set(), []
     for p in params:
@@ -75,7 +88,7 @@ class BaseSolution:
         shape = coords[0].shape
         fp = self._fused()
         u, _, _ = fp.forward([c.reshape(-1) for c in coords], want_u=True, want_residual=False)
-        us = [u[k].reshape(-1, 1) if no_reshape else u[k].reshape(shape) for k in range(u.shape[0])]
+        us = _functions(fp.tp, u, None if no_reshape else shape)
         if to_numpy:
             us = [x.detach().cpu().numpy() for x in us]
         return us if len(self.nets) > 1 else us[0]
@@ -253,7 +266,7 @@ class BaseSolver:
         if not self.metrics_fn:
             return
         u, _, _ = self.problem.forward(coords, want_u=True, want_residual=False, repack=False)
-        funcs = [u[k].reshape(-1, 1) for k in range(u.shape[0])]
+        funcs = _functions(self.problem.tp, u)
         cols = [c.reshape(-1, 1) for c in coords]
         for name, fn in self.metrics_fn.items():
             acc[name] += float(fn(*funcs, *cols).item())
@@ -287,7 +300,7 @@ class BaseSolver:
                 cols = [c.reshape(-1, 1) for c in coords]
                 u, r, _ = fp.forward(coords, want_u=True, want_residual=True, repack=False)
                 res = r.t().contiguous().requires_grad_(key == "train")      # (N, n_eq) like torch.cat(residuals, 1)
-                funcs = [u[k].reshape(-1, 1) for k in range(u.shape[0])]
+                funcs = _functions(fp.tp, u)
                 loss = self._custom_loss(res, funcs, cols) + self.additional_loss(res, funcs, cols)
                 if key == "train":
                     loss.backward()                                          # only to get dL/dr on the tiny leaf

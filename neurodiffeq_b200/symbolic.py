@@ -414,6 +414,53 @@ class Sym:
         return f"Sym#{self.idx}<{self.op}{'' if self.imm is None else ':' + str(self.imm)}>"
 
 
+class SymColumns:
+    """An (N, k) block of traced columns -- what ``EnsembleCondition.enforce`` returns for a k-output network
+    (reference conditions.py:197-202 concatenates the re-parameterised columns).  Supports what user code does with such
+    a tensor: ``u[:, i]``, ``u[:, i:i+1]`` (a column = a :class:`Sym`), ``u[:, i:j]`` (a narrower block), ``u.shape``."""
+
+    def __init__(self, cols):
+        self.cols = tuple(cols)
+        if not self.cols or not all(isinstance(c, Sym) for c in self.cols):
+            raise TypeError("SymColumns needs at least one traced column")
+
+    @property
+    def g(self):
+        return self.cols[0].g
+
+    @property
+    def shape(self):
+        return (-1, len(self.cols))
+
+    def dim(self):
+        return 2
+
+    def size(self, d=None):
+        return self.shape if d is None else self.shape[d]
+
+    def __len__(self):
+        raise TypeError("the number of sample points of a traced block is not known at trace time")
+
+    def __getitem__(self, item):
+        if not (isinstance(item, tuple) and len(item) == 2 and item[0] == slice(None)):
+            raise NotImplementedError("traced (N, k) blocks support column indexing only: u[:, i] or u[:, i:j]")
+        sel = item[1]
+        if isinstance(sel, int):
+            return self.cols[sel]
+        if isinstance(sel, slice):
+            picked = self.cols[sel]
+        elif isinstance(sel, (list, tuple)):
+            picked = tuple(self.cols[i] for i in sel)
+        else:
+            raise NotImplementedError(f"column selector {sel!r} on a traced block")
+        if len(picked) == 0:
+            raise IndexError("empty column selection")
+        return picked[0] if len(picked) == 1 else SymColumns(picked)
+
+    def __repr__(self):
+        return f"SymColumns({len(self.cols)})"
+
+
 class _SymShape(tuple):
     """Shape of a traced (N,1) column: compares equal to any other traced shape; index 1 is 1."""
 
@@ -480,7 +527,7 @@ def _dispatch_function(name, args, kwargs):
 
 
 def is_symbolic(*xs):
-    return any(isinstance(x, Sym) for x in xs)
+    return any(isinstance(x, (Sym, SymColumns)) for x in xs)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

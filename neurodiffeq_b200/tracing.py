@@ -84,13 +84,24 @@ class TracedProblem:
         g.n_sampled = n_coords
         self.n_sampled = n_coords
         coords = [g.coord(i) for i in range(n_coords)]
-        funcs = []
+        func_args, funcs, self.func_rows = [], [], []     # func_rows[k]: rows of u that make up function k (1 unless ensemble)
         for k, (net, cond) in enumerate(zip(nets, conditions)):
             cc = coords if coords_for_condition is None else coords_for_condition(k, cond, coords)
-            funcs.append(g.lift(cond.enforce(net, *cc)))
-        res = diff_eqs(*funcs, *coords) if diff_eqs is not None else []   # None: solution-only problem (u, no residual)
+            f = cond.enforce(net, *cc)
+            if isinstance(f, S.SymColumns):          # EnsembleCondition: one function = an (N, k) block of columns
+                func_args.append(f)
+                self.func_rows.append(list(range(len(funcs), len(funcs) + len(f.cols))))
+                funcs += list(f.cols)
+            else:
+                f = g.lift(f)
+                func_args.append(f)
+                self.func_rows.append([len(funcs)])
+                funcs.append(f)
+        res = diff_eqs(*func_args, *coords) if diff_eqs is not None else []   # None: solution-only problem (u, no residual)
         if isinstance(res, S.Sym) or not hasattr(res, "__len__"):
             res = [res]
+        if any(isinstance(r, S.SymColumns) for r in res):
+            raise NotImplementedError("a residual must be one (N, 1) column per equation; got a traced (N, k) block")
         residuals = [g.lift(r) for r in res]
         # constant coordinates created by the conditions (network evaluated at a boundary) follow the sampled ones; for the
         # kernels they are ordinary coordinate arrays (filled with the constant by the engine)

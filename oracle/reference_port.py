@@ -124,6 +124,18 @@ class NoCondition(_Condition):  # :205-222
         return out
 
 
+class EnsembleCondition(_Condition):  # :157-202
+    def __init__(self, *sub_conditions, force=False):
+        super().__init__()
+        self.conditions = sub_conditions
+
+    def parameterize(self, out, *coords):  # column i of the network output goes through sub-condition i
+        if out.shape[1] != len(self.conditions):
+            raise ValueError(f"number of output units ({out.shape[1]}) differs from number of conditions "
+                             f"({len(self.conditions)})")
+        return torch.cat([c.parameterize(out[:, i].view(-1, 1), *coords) for i, c in enumerate(self.conditions)], dim=1)
+
+
 class IVP(_Condition):  # :225-267
     def __init__(self, t_0, u_0=None, u_0_prime=None):
         super().__init__()
@@ -292,7 +304,7 @@ class DirichletBVPSpherical(_Condition):  # :887-956
 
 NAMESPACE = types.SimpleNamespace(
     diff=diff, grad=grad, div=div, curl=curl, laplacian=laplacian, spherical_laplacian=spherical_laplacian,
-    FCNN=FCNN, SinActv=SinActv, NoCondition=NoCondition, IVP=IVP, BundleIVP=BundleIVP,
+    FCNN=FCNN, SinActv=SinActv, NoCondition=NoCondition, EnsembleCondition=EnsembleCondition, IVP=IVP, BundleIVP=BundleIVP,
     DirichletBVP2D=DirichletBVP2D, IBVP1D=IBVP1D, DoubleEndedBVP1D=DoubleEndedBVP1D,
     DirichletBVPSpherical=DirichletBVPSpherical)
 
@@ -330,7 +342,7 @@ def evaluate(nets, conditions, diff_eqs, coords_soa, dtype=torch.float64, backwa
             p.grad = None
     coords = [torch.as_tensor(c, dtype=dtype).reshape(-1, 1).requires_grad_(True) for c in coords_soa]
     funcs, residual, loss = closure(nets, conditions, diff_eqs, coords, backward=backward)
-    out = dict(u=torch.stack([f.detach()[:, 0] for f in funcs]).numpy(), residual=residual.detach().numpy().T.copy(),
+    out = dict(u=torch.cat([f.detach().t() for f in funcs]).numpy(), residual=residual.detach().numpy().T.copy(),   # ensemble: k rows
                loss=float(loss.detach()))
     if backward:
         out["grads"] = [p.grad.detach().numpy().copy() for m in mods for p in m.parameters()]

@@ -15,7 +15,7 @@ def product_namespace():
     return types.SimpleNamespace(
         diff=diff, FCNN=FCNN, SinActv=SinActv, IVP=c.IVP, BundleIVP=c.BundleIVP, DirichletBVP2D=c.DirichletBVP2D,
         IBVP1D=c.IBVP1D, DirichletBVPSpherical=c.DirichletBVPSpherical, NoCondition=c.NoCondition,
-        DoubleEndedBVP1D=c.DoubleEndedBVP1D,
+        DoubleEndedBVP1D=c.DoubleEndedBVP1D, EnsembleCondition=c.EnsembleCondition,
         spherical_laplacian=ops.spherical_laplacian, laplacian=ops.laplacian, grad=ops.grad, div=ops.div,
         curl=ops.curl)
 

@@ -32,7 +32,8 @@ def trace(key):
 
 EXPECTED_CHANNELS = {"c1": (1, 0), "c2": (2, 2), "c3": (2, 1), "c4": (3, 3), "c5": (1, 0),
                      # Neumann ends: the network is also evaluated at a constant coordinate; heat: x, t, boundary, t+boundary
-                     "x1": (4, 4), "x2": (4, 4), "x3": (2, 1), "x4": (2, 1), "x5": (3, 1), "x6": (1, 1)}
+                     "x1": (4, 4), "x2": (4, 4), "x3": (2, 1), "x4": (2, 1), "x5": (3, 1), "x6": (1, 1),
+                     "x7": (1, 0)}   # EnsembleCondition: one 2-output network, the function is an (N, 2) block
 
 
 @pytest.mark.parametrize("key", workloads.NAMES + workloads.EXTRA_NAMES)

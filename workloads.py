@@ -187,6 +187,22 @@ def _bvp(nd, name, kw):
                     diff_eqs, 1, 4096, n_inst * _fcnn_flops((1, 32, 32, 1), 3), None)
 
 
+def _ensemble(nd):
+    """One 2-output network, EnsembleCondition of two IVPs (reference conditions.py:157-202): u' = v, v' = -u."""
+    def make_nets():
+        return [nd.FCNN(n_input_units=1, n_output_units=2, hidden_units=(32, 32), actv=nd.SinActv)]
+
+    def make_conditions():
+        return [nd.EnsembleCondition(nd.IVP(t_0=0.0, u_0=0.0), nd.IVP(t_0=0.0, u_0=1.0))]
+
+    def diff_eqs(uv, t):
+        u, v = uv[:, 0:1], uv[:, 1:2]
+        return [nd.diff(u, t) - v, nd.diff(v, t) + u]
+
+    return Workload("x7_ensemble_oscillator", "Solver1D", ("t",), ((0.0, 6.0),), [((1, 32, 32, 2), "sin")], make_nets,
+                    make_conditions, diff_eqs, 2, 4096, _fcnn_flops((1, 32, 32, 2), 2), None)
+
+
 _EXTRA = {
     "x1": lambda nd: _heat(nd, "x1_heat_dirichlet_neumann", "right"),
     "x2": lambda nd: _heat(nd, "x2_heat_neumann_dirichlet", "left"),
@@ -194,6 +210,7 @@ _EXTRA = {
     "x4": lambda nd: _bvp(nd, "x4_bvp_neumann_dirichlet", dict(x_min_prime=-0.5, x_max_val=0.25)),
     "x5": lambda nd: _bvp(nd, "x5_bvp_neumann_neumann", dict(x_min_prime=-0.5, x_max_prime=0.5)),
     "x6": lambda nd: _bvp(nd, "x6_bvp_dirichlet_dirichlet", dict(x_min_val=1.0, x_max_val=0.25)),
+    "x7": _ensemble,
 }
 _BUILDERS = {"c1": _c1, "c2": _c2, "c3": _c3, "c4": _c4, "c5": _c5}
 NAMES = tuple(_BUILDERS)          # BASELINE.json configs
