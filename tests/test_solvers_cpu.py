@@ -72,3 +72,48 @@ def test_custom_loss_callable_and_solution_cpu():
     u = sol(x, to_numpy=True)
     assert u.shape == (3,) and abs(u[0] - 1.0) < 1e-12     # Dirichlet end of x3: u(0) = 1 for any weights
     del l0
+
+
+def test_solution_residuals_metrics_and_early_stop_cpu():
+    """The solver API surface of the reference (solvers.py:443-497, 606-720) on the stand-in engine: solution / residual
+    evaluation with reshaping, `best` networks, metrics histories, callbacks with early stopping, multi-batch epochs."""
+    wl, solver, nets, coords_np = make_solver("c2", 100, metrics={"mean_u": lambda u, x, y: u.mean()})
+    calls = []
+
+    def stopper(s):
+        calls.append(s.local_epoch)
+        if s.local_epoch == 2:
+            s._stop_training = True
+
+    solver.fit(10, callbacks=[stopper], tqdm_file=None)
+    assert calls == [1, 2] and solver.global_epoch == 2
+    assert len(solver.metrics_history["train__mean_u"]) == 2 and len(solver.metrics_history["valid__mean_u"]) == 2
+    xs, ys = np.linspace(0, 1, 5), np.linspace(0, 1, 4)
+    X, Y = np.meshgrid(xs, ys, indexing="ij")
+    u = solver.get_solution(best=False)(X, Y, to_numpy=True)
+    assert u.shape == X.shape
+    np.testing.assert_allclose(u[0, :], np.sin(np.pi * ys), atol=1e-6)       # Dirichlet data met by construction
+    np.testing.assert_allclose(u[-1, :], 0, atol=1e-6)
+    r = solver.get_residuals(X, Y, to_numpy=True, best=False)
+    assert r.shape == X.shape and np.isfinite(r).all()
+    rb = solver.get_residuals(torch.tensor(X), torch.tensor(Y), best=True)
+    assert isinstance(rb, torch.Tensor) and rb.shape == X.shape
+    assert solver.get_solution(best=True)(X, Y, to_numpy=True, no_reshape=True).shape == (X.size, 1)
+    # two batches per epoch: gradients add up (reference solvers.py:360-362)
+    wl, s2, nets2, _ = make_solver("c2", 60, n_batches_train=2)
+    s2.run_train_epoch()
+    g2 = s2.problem.grad.clone()
+    wl, s1, nets1, _ = make_solver("c2", 60)
+    s1.run_train_epoch()
+    assert torch.allclose(g2, 2 * s1.problem.grad, rtol=1e-9, atol=1e-12)
+
+
+def test_ensemble_solution_is_a_block_cpu():
+    wl, solver, nets, coords_np = make_solver("x7", 80)
+    solver.fit(2, tqdm_file=None)
+    t = torch.linspace(0.0, 1.0, 6)
+    uv = solver.get_solution(best=False)(t, to_numpy=True)
+    assert uv.shape == (6, 2)
+    np.testing.assert_allclose(uv[0], [0.0, 1.0], atol=1e-12)              # the two initial values
+    r = solver.get_residuals(t, best=False)
+    assert isinstance(r, list) and len(r) == 2 and r[0].shape == (6,)
