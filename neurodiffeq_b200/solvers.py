@@ -150,9 +150,11 @@ class BaseSolver:
 
         self.optimizer = optimizer if optimizer else torch.optim.Adam(
             _unique(chain.from_iterable(n.parameters() for n in self.nets)))
-        if _requires_closure(self.optimizer):
-            raise NotImplementedError("closure-based optimizers (LBFGS, reference solvers.py:398-400) are not "
-                                      "supported by the fused solvers yet")
+        if self.n_batches["valid"] == 0 and _requires_closure(self.optimizer):   # reference solvers.py:196-202
+            warnings.warn(f"Setting n_batches_valid=0 will update lowest_loss and best_net with training loss "
+                          f"instead of validation loss. This is a problem for {self.optimizer.__class__} optimizer "
+                          f"because it updates the parameters before the training loss computed. "
+                          f"This leads to potentially worse solution in `best_net`!", RuntimeWarning)
         self.best_nets_theta = None
         self.lowest_loss = None
         self.local_epoch = 0
@@ -271,6 +273,52 @@ class BaseSolver:
         for name, fn in self.metrics_fn.items():
             acc[name] += float(fn(*funcs, *cols).item())
 
+    def _run_train_epoch_with_closure(self):
+        """Closure-based optimizers (LBFGS), reference solvers.py:369-400: one ``optimizer.step(closure)`` PER BATCH; the
+        closure zeroes the gradients, evaluates loss and gradient on that batch (fused kernels) and returns the loss; the
+        recorded batch loss is that of the closure's last evaluation."""
+        key, fp = "train", self.problem
+        metric_values = {name: 0.0 for name in self.metrics_fn}
+        n_b = self.n_batches[key]
+        epoch_loss = 0.0
+        for _ in range(n_b):
+            coords = self._to_device(self._generate_batch(key))
+            denom = float(self._n_global * fp.n_eq)
+            last = {}
+
+            def closure():
+                fp.gradbuf.zero_()
+                fp.pack()                                    # the optimizer moved the parameters since the last call
+                if self._custom_loss is None:
+                    fp.residual_grad(coords, n_global=self._n_global, sumsq_out=fp.sumsq, repack=False)
+                    if self._dist is not None:
+                        self._dist.all_reduce(fp.gradbuf)    # [grad | sum r^2]: identical on every rank afterwards
+                    loss = (fp.sumsq / denom).reshape(()).clone()
+                else:
+                    cols = [c.reshape(-1, 1) for c in coords]
+                    u, r, _ = fp.forward(coords, want_u=True, want_residual=True, repack=False)
+                    res = r.t().contiguous().requires_grad_(True)
+                    funcs = _functions(fp.tp, u)
+                    loss = self._custom_loss(res, funcs, cols) + self.additional_loss(res, funcs, cols)
+                    loss.backward()
+                    fp.residual_grad(coords, rbar=res.grad.t().contiguous(), sumsq_out=fp.sumsq, repack=False)
+                    loss = loss.detach().reshape(()).to(fp.sumsq.dtype)
+                    if self._dist is not None:
+                        fp.sumsq.copy_(loss.reshape(1))
+                        self._dist.all_reduce(fp.gradbuf)
+                        loss = (fp.sumsq / self._dist.get_world_size()).reshape(()).clone()
+                self._eval_metrics(coords, metric_values)    # inside the closure, like the reference (:376-378)
+                last["loss"] = loss
+                return loss
+
+            self._do_optimizer_step(closure=closure)
+            epoch_loss += float(last["loss"].item())
+        self._update_history(epoch_loss / n_b, "loss", key)
+        if self.n_batches["valid"] == 0:
+            self._update_best(key)
+        for name in self.metrics_fn:
+            self._update_history(metric_values[name] / n_b, name, key)
+
     def _run_epoch(self, key):
         if self.n_batches[key] <= 0:
             return
@@ -278,6 +326,8 @@ class BaseSolver:
         fp = self.problem
         if not fp.parameters_linked():
             fp.relink()
+        if key == "train" and _requires_closure(self.optimizer):
+            return self._run_train_epoch_with_closure()
         metric_values = {name: 0.0 for name in self.metrics_fn}
         n_b = self.n_batches[key]
         loss_acc = torch.zeros(1, dtype=torch.float32, device=self.device)

@@ -117,3 +117,45 @@ def test_ensemble_solution_is_a_block_cpu():
     np.testing.assert_allclose(uv[0], [0.0, 1.0], atol=1e-12)              # the two initial values
     r = solver.get_residuals(t, best=False)
     assert isinstance(r, list) and len(r) == 2 and r[0].shape == (6,)
+
+
+def test_lbfgs_closure_mode_cpu():
+    """LBFGS (reference solvers.py:398-400): one step(closure) per batch; the closure re-evaluates loss and gradient.
+    Same optimizer, same closure semantics on the oracle (autograd) -> same parameters."""
+    from oracle import reference_port as oracle
+    key, n, epochs = "x6", 60, 3
+    wl = workloads.build(__import__("helpers").product_namespace(), key)
+    torch.manual_seed(0)
+    nets = wl.make_nets()
+    opt = torch.optim.LBFGS([p for m in nets for p in m.parameters()], lr=0.5, max_iter=4, history_size=5)
+    import neurodiffeq_b200.solvers as Sv
+    from neurodiffeq_b200.generators import PredefinedGenerator
+    coords_np = workloads.sample_coords(wl, n, seed=21)
+    gen = PredefinedGenerator(*[c for c in coords_np])
+    params0 = get_params(nets)
+    solver = Sv.Solver1D(wl.diff_eqs, wl.make_conditions(), nets=nets, train_generator=gen, valid_generator=gen,
+                         n_batches_valid=1, optimizer=opt)
+    solver.fit(epochs, tqdm_file=None)
+
+    owl = workloads.build(oracle.NAMESPACE, key)
+    onets, oconds = owl.make_nets(), owl.make_conditions()
+    oracle.load_params(onets, params0, dtype=torch.float64)
+    oparams = [p for m in oracle.distinct_modules(onets) for p in m.parameters()]
+    oopt = torch.optim.LBFGS(oparams, lr=0.5, max_iter=4, history_size=5)
+    ref_losses = []
+    for _ in range(epochs):
+        last = {}
+
+        def closure():
+            oopt.zero_grad()
+            cols = [torch.as_tensor(c, dtype=torch.float64).reshape(-1, 1).requires_grad_(True) for c in coords_np]
+            _, _, loss = oracle.closure(onets, oconds, owl.diff_eqs, cols)
+            last["loss"] = float(loss.detach())
+            return loss
+
+        oopt.step(closure)
+        ref_losses.append(last["loss"])
+    np.testing.assert_allclose(solver.metrics_history["train_loss"], ref_losses, rtol=1e-5)
+    for a, b in zip(get_params(nets), [p.detach().numpy() for p in oparams]):
+        np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-8)
+    assert len(solver.metrics_history["valid_loss"]) == epochs
