@@ -226,6 +226,18 @@ class FusedProblem:
                 net.b_off[l] = self._offset_of[id(lin.bias)]
         self.spec = sp
 
+    def enable_function_adjoints(self):
+        """Prepare for losses that depend on the functions u as well as on the residuals (``ubar`` in
+        :meth:`residual_grad`): upload that train program and make the value file large enough for it."""
+        if getattr(self, "_prog_train_ext_u", None) is None:
+            p = self.tp.prog_train_ext_u
+            self._prog_train_ext_u = torch.from_numpy(p.code.copy()).to(self.device)
+            if p.n_slots > self.spec.n_slots:
+                self.spec.n_slots = p.n_slots
+                self._sizes_cache.clear()
+                self._graphs.clear()
+        return self._prog_train_ext_u
+
     @property
     def prog_train_ext(self):
         if self._prog_train_ext is None:
@@ -308,10 +320,13 @@ class FusedProblem:
         self.kernel_launches += 2 if want_sumsq else 1
         return u, r, (self.sumsq if want_sumsq else None)
 
-    def residual_grad(self, coords, n_global=None, want_residual=False, rbar=None, sumsq_out=None, repack=True):
-        """K1(train)+K2+K2b: ``grad`` += d/dtheta mean(r^2) (or of the caller's loss when ``rbar`` = dL/dr is given);
+    def residual_grad(self, coords, n_global=None, want_residual=False, rbar=None, sumsq_out=None, repack=True, ubar=None):
+        """K1(train)+K2+K2b: ``grad`` += d/dtheta mean(r^2) (or of the caller's loss when ``rbar`` = dL/dr [n_eq, N] and,
+        for losses that also depend on the functions, ``ubar`` = dL/du [n_funcs, N] are given);
         returns (sum r^2 device tensor, residual or None).  mean(r^2) = sumsq / (N_global * n_eq)."""
         n = coords[0].numel()
+        if ubar is not None:
+            self.enable_function_adjoints()      # may enlarge spec.n_slots: before any size / plan query
         self._ensure_buffers(n, True)
         if repack:
             self.pack()
@@ -322,12 +337,20 @@ class FusedProblem:
         if sumsq_out is None:
             sumsq_out = self.sumsq
             sumsq_out.zero_()
+        if ubar is not None and rbar is None:
+            raise ValueError("ubar (dL/du) needs rbar (dL/dr) as well")
         prog = self.prog_train if rbar is None else self.prog_train_ext
         prog_len = len(self.tp.prog_train if rbar is None else self.tp.prog_train_ext)
         if rbar is not None:
             rbar = rbar.detach().to(self.device, torch.float32).contiguous()
             if tuple(rbar.shape) != (self.n_eq, n):
                 raise ValueError(f"rbar must have shape ({self.n_eq}, {n})")
+        if ubar is not None:   # the external cotangent buffer becomes [dL/dr | dL/du]
+            ubar = ubar.detach().to(self.device, torch.float32).contiguous()
+            if tuple(ubar.shape) != (self.n_funcs, n):
+                raise ValueError(f"ubar must have shape ({self.n_funcs}, {n})")
+            prog, prog_len = self.enable_function_adjoints(), len(self.tp.prog_train_ext_u)
+            rbar = torch.cat([rbar, ubar], dim=0).contiguous()
         _check(self.lib.pj_forward_train(ctypes.byref(self.spec), prog.data_ptr(), prog_len, *self._prog_w_args(), ptrs, n,
                                          self.pack_buf.data_ptr(), ctypes.c_float(scale),
                                          rbar.data_ptr() if rbar is not None else None,

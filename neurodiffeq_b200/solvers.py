@@ -49,6 +49,10 @@ def _functions(tp, u, shape=None):
     return out
 
 
+def _grad_or_zeros(leaf):
+    return leaf.grad if leaf.grad is not None else torch.zeros_like(leaf)
+
+
 def _unique(params):
     seen, out = set(), []
     for p in params:
@@ -115,8 +119,6 @@ class BaseSolver:
                           FutureWarning)
         if analytic_solutions:
             raise NotImplementedError("`analytic_solutions` is deprecated in the reference; pass a `metrics` dict")
-        if type(self).additional_loss is not BaseSolver.additional_loss:
-            raise NotImplementedError("overriding `additional_loss` is not supported by the fused solvers yet")
         self.diff_eqs = diff_eqs
         self.conditions = conditions
         self.n_funcs = len(conditions)
@@ -183,13 +185,16 @@ class BaseSolver:
 
     def _set_loss_fn(self, criterion):
         # None / 'l2' / nn.MSELoss: the fused mean-squared residual (reference solvers.py:216-226, losses.py:10-12).
-        # Any other callable (residual, funcs, coords) -> scalar is differentiated by autograd w.r.t. the residual
-        # only; dL/dr is then handed to the kernels (funcs / coords are passed detached).
+        # Any other callable (residual, funcs, coords) -> scalar is differentiated by autograd w.r.t. the residual matrix
+        # and the function values (small leaf tensors); dL/dr and dL/du are then handed to the kernels as external
+        # cotangents of the traced train program.  Coordinates are passed detached (they carry no parameters).
         self._custom_loss = None
         self._h1 = False
         if criterion is None or (isinstance(criterion, str) and criterion.lower() == "l2") \
                 or isinstance(criterion, nn.MSELoss):
             self.loss_fn = lambda r, f, x: (r ** 2).mean()
+            if type(self).additional_loss is not BaseSolver.additional_loss:
+                self._custom_loss = self.loss_fn    # an overridden additional_loss (reference solvers.py:587-604) needs autograd
         elif isinstance(criterion, nn.modules.loss._Loss):
             self.loss_fn = lambda r, f, x: criterion(r, torch.zeros_like(r))
             self._custom_loss = self.loss_fn
@@ -298,10 +303,12 @@ class BaseSolver:
                     cols = [c.reshape(-1, 1) for c in coords]
                     u, r, _ = fp.forward(coords, want_u=True, want_residual=True, repack=False)
                     res = r.t().contiguous().requires_grad_(True)
+                    u = u.requires_grad_(True)
                     funcs = _functions(fp.tp, u)
                     loss = self._custom_loss(res, funcs, cols) + self.additional_loss(res, funcs, cols)
                     loss.backward()
-                    fp.residual_grad(coords, rbar=res.grad.t().contiguous(), sumsq_out=fp.sumsq, repack=False)
+                    fp.residual_grad(coords, rbar=_grad_or_zeros(res).t().contiguous(), ubar=u.grad, sumsq_out=fp.sumsq,
+                                     repack=False)
                     loss = loss.detach().reshape(()).to(fp.sumsq.dtype)
                     if self._dist is not None:
                         fp.sumsq.copy_(loss.reshape(1))
@@ -350,11 +357,13 @@ class BaseSolver:
                 cols = [c.reshape(-1, 1) for c in coords]
                 u, r, _ = fp.forward(coords, want_u=True, want_residual=True, repack=False)
                 res = r.t().contiguous().requires_grad_(key == "train")      # (N, n_eq) like torch.cat(residuals, 1)
+                u = u.requires_grad_(key == "train")                         # leaf: dL/du if the loss looks at the functions
                 funcs = _functions(fp.tp, u)
                 loss = self._custom_loss(res, funcs, cols) + self.additional_loss(res, funcs, cols)
                 if key == "train":
-                    loss.backward()                                          # only to get dL/dr on the tiny leaf
-                    fp.residual_grad(coords, rbar=res.grad.t().contiguous(), sumsq_out=fp.sumsq, repack=False)
+                    loss.backward()                                          # only to get dL/dr, dL/du on the tiny leaves
+                    fp.residual_grad(coords, rbar=_grad_or_zeros(res).t().contiguous(), ubar=u.grad, sumsq_out=fp.sumsq,
+                                     repack=False)
                 loss_acc += loss.detach().reshape(1).to(torch.float32)
             self._eval_metrics(coords, metric_values)
         if self._dist is not None:   # one collective per epoch phase: [grad | loss] summed over the ranks

@@ -212,10 +212,12 @@ class TracedProblem:
         self.weight_exprs = [(n * n2 + d, weights.get(n, [zero] * n2)[d]) for n in range(len(self.nets))
                              for d in range(n2)]
 
-    def _train_program(self, external_rbar):
+    def _train_program(self, external_rbar, with_func_adjoint=False):
         g = self.graph
         if external_rbar:
             cots = [(r, g.rbar(e)) for e, r in enumerate(self.residuals)]
+            if with_func_adjoint:   # rows n_eq .. n_eq + n_funcs - 1 of the external buffer carry dL/du
+                cots += [(f, g.rbar(self.n_eq + k)) for k, f in enumerate(self.funcs)]
         else:  # L = scale/2 * sum r^2 with scale = 2/(N n_eq)  ->  dL/dr = scale * r
             cots = [(r, g.mul(g.param(S.PARAM_LOSS_SCALE), r)) for r in self.residuals]
         adj = S.reverse_gradients(cots)
@@ -239,6 +241,14 @@ class TracedProblem:
             return coords
         extra = np.repeat(np.asarray(self.const_coords, dtype=coords.dtype)[:, None], coords.shape[1], axis=1)
         return np.concatenate([coords, extra], axis=0)
+
+    @property
+    def prog_train_ext_u(self):
+        """Train program for a loss that depends on the residuals AND on the functions: the external cotangent buffer
+        has n_eq + n_funcs rows, [dL/dr | dL/du]."""
+        if getattr(self, "_prog_train_ext_u", None) is None:
+            self._prog_train_ext_u = self._train_program(external_rbar=True, with_func_adjoint=True)
+        return self._prog_train_ext_u
 
     def direction_matrix(self):
         """[n1, n_coords] float32: direction vectors of the first-order channels."""

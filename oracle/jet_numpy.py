@@ -109,7 +109,7 @@ def backward(weights, act, x_in, dirs_in, n2, z_store, ybar, wl=None):
     return gW, gb
 
 
-def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True, rbar=None):
+def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True, rbar=None, ubar=None):
     """Evaluate a TracedProblem end to end in float64.
 
     ``params_per_net``: list (per network INSTANCE of ``tp.nets``; instances of one module get the same arrays) of
@@ -145,9 +145,13 @@ def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True, rbar=N
         if rbar is None:   # L = mean(r^2) over the global batch
             _, r2, seeds = S.evaluate_program(tp.prog_train, coords, y_rows, params=[scale], n_r=tp.n_eq,
                                               n_seed=tp.n_yrows)
-        else:              # externally supplied dL/dr [n_eq, N] (custom loss functions)
+        elif ubar is None:  # externally supplied dL/dr [n_eq, N] (custom loss functions)
             _, r2, seeds = S.evaluate_program(tp.prog_train_ext, coords, y_rows, rbar=np.asarray(rbar, dtype=np.float64),
                                               params=[scale], n_r=tp.n_eq, n_seed=tp.n_yrows)
+        else:               # ... and dL/du [n_funcs, N] for losses that also depend on the functions
+            ext = np.concatenate([np.asarray(rbar, dtype=np.float64), np.asarray(ubar, dtype=np.float64)], axis=0)
+            _, r2, seeds = S.evaluate_program(tp.prog_train_ext_u, coords, y_rows, rbar=ext, params=[scale], n_r=tp.n_eq,
+                                              n_seed=tp.n_yrows)
         assert np.allclose(r2, r)
         by_module = {}   # instances that share a module (network evaluated at a boundary too) add up, like autograd
         for k, nd in enumerate(tp.nets):

@@ -64,9 +64,10 @@ class CpuFusedProblem:
         return (torch.from_numpy(out["u"]) if want_u else None, torch.from_numpy(out["residual"]) if want_residual else None,
                 self.sumsq if want_sumsq else None)
 
-    def residual_grad(self, coords, n_global=None, want_residual=False, rbar=None, sumsq_out=None, repack=True):
+    def residual_grad(self, coords, n_global=None, want_residual=False, rbar=None, sumsq_out=None, repack=True, ubar=None):
         out = jet_numpy.run_traced(self.tp, self._per_instance(), self._np(coords), n_global=n_global,
-                                   rbar=None if rbar is None else rbar.detach().numpy())
+                                   rbar=None if rbar is None else rbar.detach().numpy(),
+                                   ubar=None if ubar is None else ubar.detach().numpy())
         with torch.no_grad():
             for g, off in zip(out["grads"], self.offsets):   # accumulate, like loss.backward()
                 self.grad[off:off + g.size] += torch.from_numpy(np.ascontiguousarray(g).reshape(-1))

@@ -159,3 +159,65 @@ def test_lbfgs_closure_mode_cpu():
     for a, b in zip(get_params(nets), [p.detach().numpy() for p in oparams]):
         np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-8)
     assert len(solver.metrics_history["valid_loss"]) == epochs
+
+
+def _oracle_training_custom(key, params, coords_np, epochs, loss_of):
+    from oracle import reference_port as oracle
+    wl = workloads.build(oracle.NAMESPACE, key)
+    nets, conds = wl.make_nets(), wl.make_conditions()
+    oracle.load_params(nets, params, dtype=torch.float64)
+    mods = oracle.distinct_modules(nets)
+    opt = torch.optim.Adam([p for m in mods for p in m.parameters()], lr=1e-3)
+    losses = []
+    for _ in range(epochs):
+        opt.zero_grad()
+        cols = [torch.as_tensor(c, dtype=torch.float64).reshape(-1, 1).requires_grad_(True) for c in coords_np]
+        funcs = [c.enforce(n, *cols) for n, c in zip(nets, conds)]
+        res = torch.cat(workloads.bundle_eq_wrapper(wl)(*funcs, *cols), dim=1)
+        loss = loss_of(res, funcs, cols)
+        loss.backward()
+        losses.append(float(loss.detach()))
+        opt.step()
+    return losses, [p.detach().numpy().copy() for m in mods for p in m.parameters()]
+
+
+def test_loss_that_depends_on_the_functions_cpu():
+    """loss_fn(residual, funcs, coords) may look at the functions (reference solvers.py:66-79): dL/du reaches the
+    parameters through the same traced program as dL/dr."""
+    def loss_fn(residual, funcs, coords):
+        u, v = funcs
+        return (residual ** 2).mean() + 0.3 * ((u - 1.0) ** 2).mean() + 0.1 * (u * v * coords[0]).mean()
+
+    key, n, epochs = "c1", 90, 4
+    wl, solver, nets, coords_np = make_solver(key, n, loss_fn=loss_fn)
+    params0 = get_params(nets)
+    solver.fit(epochs, tqdm_file=None)
+    ref_losses, ref_params = _oracle_training_custom(key, params0, coords_np, epochs, loss_fn)
+    np.testing.assert_allclose(solver.metrics_history["train_loss"], ref_losses, rtol=5e-7)
+    for a, b in zip(get_params(nets), ref_params):
+        np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-11)
+
+
+def test_overridden_additional_loss_cpu():
+    """`additional_loss` (reference solvers.py:587-604) as a subclass hook, here a penalty on the solution's mean."""
+    import neurodiffeq_b200.solvers as Sv
+    from neurodiffeq_b200.generators import PredefinedGenerator
+
+    class Penalised(Sv.Solver1D):
+        def additional_loss(self, residual, funcs, coords):
+            return 0.5 * funcs[0].mean() ** 2
+
+    key, n, epochs = "x6", 70, 4
+    wl = workloads.build(__import__("helpers").product_namespace(), key)
+    torch.manual_seed(0)
+    nets = wl.make_nets()
+    coords_np = workloads.sample_coords(wl, n, seed=21)
+    gen = PredefinedGenerator(*[c for c in coords_np])
+    params0 = get_params(nets)
+    solver = Penalised(wl.diff_eqs, wl.make_conditions(), nets=nets, train_generator=gen, valid_generator=gen, n_batches_valid=1)
+    solver.fit(epochs, tqdm_file=None)
+    ref_losses, ref_params = _oracle_training_custom(
+        key, params0, coords_np, epochs, lambda r, f, x: (r ** 2).mean() + 0.5 * f[0].mean() ** 2)
+    np.testing.assert_allclose(solver.metrics_history["train_loss"], ref_losses, rtol=5e-7)
+    for a, b in zip(get_params(nets), ref_params):
+        np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-11)
