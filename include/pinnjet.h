@@ -108,8 +108,10 @@ int pj_forward(const PjSpec* spec, const int32_t* prog_eval /*device*/, int32_t 
 
 /* Training forward: residual program + seeds dL/d(jet) + z-jets into the workspace for pj_backward.
  * loss = loss_scale/2 * sum r^2 with loss_scale = 2/(N_global*n_eq)  (solvers.py:218: (r**2).mean()).
- * If rbar != NULL it is float[n_eq][N] = dL/dr supplied by the caller (custom loss_fn, solvers.py:216-226) and the
- * program must be the external-cotangent variant.  resid_out may be NULL.  *sumsq_out += sum r^2.             */
+ * If rbar != NULL it is float[R][N], the external cotangents the program's OP_RBAR instructions index: n_eq rows of
+ * dL/dr supplied by the caller (custom loss_fn, solvers.py:216-226), optionally followed by n_funcs rows of dL/du for
+ * losses that also look at the functions; the program must be the matching external-cotangent variant.
+ * resid_out may be NULL.  *sumsq_out += sum r^2.                                                              */
 int pj_forward_train(const PjSpec* spec, const int32_t* prog_train /*device*/, int32_t prog_len,
                      const int32_t* prog_w /*device or NULL*/, int32_t prog_w_len,
                      const float* const* coords, int64_t n_points, const float* theta_pack,
