@@ -1,0 +1,55 @@
+"""Optimizers that work on the engine's FLAT parameter / gradient buffers.
+
+The fused engine keeps every ``nn.Parameter`` as a view into one flat ``theta`` tensor and every ``.grad`` as a view into one
+flat ``grad`` tensor (``engine.FusedProblem._adopt_parameters``).  ``torch.optim.Adam`` over the individual parameters walks
+a Python list of tensors and their state dicts every step; :class:`FlatAdam` applies the same update (Adam, Kingma & Ba;
+the algorithm of ``torch.optim.Adam`` with ``amsgrad=False, weight_decay=0, maximize=False``, reference default
+``solvers.py:182``) to the flat buffers with a handful of elementwise kernels, independent of the number of layers.
+
+Opt-in::
+
+    solver = Solver2D(...)
+    solver.optimizer = FlatAdam.for_solver(solver, lr=1e-3)
+"""
+import math
+
+import torch
+
+
+class FlatAdam(torch.optim.Optimizer):
+    def __init__(self, theta, grad, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        if theta.dim() != 1 or grad.shape != theta.shape:
+            raise ValueError("FlatAdam expects the flat parameter buffer and its flat gradient buffer")
+        if not 0.0 <= lr or not 0.0 <= eps or not (0.0 <= betas[0] < 1.0 and 0.0 <= betas[1] < 1.0):
+            raise ValueError("invalid Adam hyper-parameters")
+        self._theta, self._grad = theta, grad
+        holder = torch.nn.Parameter(theta.detach(), requires_grad=False)   # param_groups / state_dict plumbing
+        super().__init__([holder], dict(lr=lr, betas=betas, eps=eps))
+        self._m = torch.zeros_like(theta)
+        self._v = torch.zeros_like(theta)
+        self._t = 0
+
+    @classmethod
+    def for_solver(cls, solver, **kw):
+        return cls(solver.problem.theta, solver.problem.grad, **kw)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        group = self.param_groups[0]
+        lr, (b1, b2), eps = group["lr"], group["betas"], group["eps"]
+        self._t += 1
+        g = self._grad
+        self._m.mul_(b1).add_(g, alpha=1.0 - b1)
+        self._v.mul_(b2).addcmul_(g, g, value=1.0 - b2)
+        bc1 = 1.0 - b1 ** self._t
+        bc2 = 1.0 - b2 ** self._t
+        denom = (self._v.sqrt() / math.sqrt(bc2)).add_(eps)
+        self._theta.addcdiv_(self._m, denom, value=-lr / bc1)
+        return loss
+
+    def zero_grad(self, set_to_none=False):
+        self._grad.zero_()
