@@ -11,6 +11,8 @@
 #   precision        fp32 kernels vs fp64 oracle vs the oracle's own fp32 run (tools/gpu_precision.py)
 #   scale2           2-GPU weak scaling of bench.py (needs gpurun --gpus 2)
 #   probes           the stand-alone tcgen05 probes under experiments/tcgen05_probe
+#   k2tc             bring-up of the experimental tensor-core reverse kernel: build `python neurodiffeq_b200/csrc/build.py
+#                    --experimental` HERE first (libpinnjet_exp.so travels with the snapshot), then parity suite + bench
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 mode=${1:-tests}; shift
@@ -66,5 +68,13 @@ case "$mode" in
     summary gpurun_out/bench_c2_g2.json gpurun_out/bench_c3_g2.json ;;
   probes)
     bash experiments/tcgen05_probe/run.sh; bash experiments/tcgen05_probe/run_wgrad.sh ;;
+  k2tc)
+    export PINNJET_LIB=$PWD/neurodiffeq_b200/csrc/libpinnjet_exp.so PINNJET_TC_BWD=1
+    ls -la $PINNJET_LIB || exit 2
+    timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "c2 or c5" > gpurun_out/pytest_gpu_k2tc.log 2>&1
+    tail -15 gpurun_out/pytest_gpu_k2tc.log
+    timeout 200 python bench.py --steps 50 --warmup 5 --cpu-seconds 0.5 --fit-epochs 0 --no-gpu-comparator \
+        > gpurun_out/bench_c2_k2tc.json 2> gpurun_out/bench_c2_k2tc.err
+    summary gpurun_out/bench_c2_k2tc.json ;;
   *) echo "unknown mode $mode"; exit 2 ;;
 esac
