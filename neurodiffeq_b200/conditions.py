@@ -21,6 +21,7 @@ import warnings
 import torch
 
 from . import symbolic as _sym
+from ._compat import renamed_arguments
 
 
 def _exp(x):
@@ -136,14 +137,9 @@ def _ivp_form(out, t, t_0, u_0, u_0_prime):
 class IVP(BaseCondition):
     """u(t0)=u0 [and u'(t0)=u0']:  u = u0 + (1-e^{-(t-t0)}) N   /   u0 + (t-t0)u0' + (1-e^{-(t-t0)})^2 N."""
 
-    def __init__(self, t_0, u_0=None, u_0_prime=None, **legacy):
+    @renamed_arguments(x_0="u_0", x_0_prime="u_0_prime")          # reference conditions.py:242
+    def __init__(self, t_0, u_0=None, u_0_prime=None):
         super().__init__()
-        if "x_0" in legacy:
-            u_0 = legacy.pop("x_0")
-        if "x_0_prime" in legacy:
-            u_0_prime = legacy.pop("x_0_prime")
-        if legacy:
-            raise TypeError(f"unexpected arguments {list(legacy)}")
         self.t_0, self.u_0, self.u_0_prime = t_0, u_0, u_0_prime
 
     def parameterize(self, output_tensor, t):
@@ -151,12 +147,9 @@ class IVP(BaseCondition):
 
 
 class BundleIVP(BaseCondition, _BundleConditionMixin):
-    def __init__(self, t_0=None, u_0=None, u_0_prime=None, bundle_param_lookup=None, **legacy):
+    @renamed_arguments(x_0="u_0", x_0_prime="u_0_prime", bundle_conditions="bundle_param_lookup")   # conditions.py:295
+    def __init__(self, t_0=None, u_0=None, u_0_prime=None, bundle_param_lookup=None):
         BaseCondition.__init__(self)
-        if "bundle_conditions" in legacy:
-            bundle_param_lookup = legacy.pop("bundle_conditions")
-        if legacy:
-            raise TypeError(f"unexpected arguments {list(legacy)}")
         _BundleConditionMixin.__init__(self, bundle_param_lookup=bundle_param_lookup,
                                        allowed_params=["t_0", "u_0", "u_0_prime"])
         self.t_0, self.u_0, self.u_0_prime = t_0, u_0, u_0_prime
@@ -174,6 +167,7 @@ def _two_point_form(out, t, t_0, u_0, t_1, u_1):
 class DirichletBVP(BaseCondition):
     """u(t0)=u0, u(t1)=u1 (reference conditions.py:398-435)."""
 
+    @renamed_arguments(x_0="u_0", x_1="u_1")                       # reference conditions.py:412
     def __init__(self, t_0, u_0, t_1, u_1):
         super().__init__()
         self.t_0, self.u_0, self.t_1, self.u_1 = t_0, u_0, t_1, u_1
@@ -183,6 +177,7 @@ class DirichletBVP(BaseCondition):
 
 
 class BundleDirichletBVP(BaseCondition, _BundleConditionMixin):
+    @renamed_arguments(bundle_conditions="bundle_param_lookup")   # reference conditions.py:363
     def __init__(self, t_0=None, u_0=None, t_1=None, u_1=None, bundle_param_lookup=None):
         BaseCondition.__init__(self)
         _BundleConditionMixin.__init__(self, bundle_param_lookup=bundle_param_lookup,

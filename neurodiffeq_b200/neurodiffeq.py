@@ -8,6 +8,7 @@ reference's eager semantics: ``order`` nested ``autograd.grad(create_graph=True)
 import torch
 
 from . import symbolic as _sym
+from ._compat import renamed_arguments
 
 
 def _check_shapes(u, t):
@@ -21,6 +22,7 @@ def _check_shapes(u, t):
                          f"got {tuple(u.shape)} != {tuple(t.shape)}")
 
 
+@renamed_arguments(x="u")
 def unsafe_diff(u, t, order=1):
     """Derivative without shape checks (reference neurodiffeq.py:6-34)."""
     if _sym.is_symbolic(u, t):
@@ -34,6 +36,7 @@ def unsafe_diff(u, t, order=1):
     return cur
 
 
+@renamed_arguments(x="u")
 def safe_diff(u, t, order=1):
     """Derivative with the (n_samples, 1) shape contract (reference neurodiffeq.py:37-60)."""
     if not _sym.is_symbolic(u, t):
@@ -43,6 +46,7 @@ def safe_diff(u, t, order=1):
     return unsafe_diff(u, t, order=order)
 
 
+@renamed_arguments(x="u")
 def diff(u, t, order=1, shape_check=True):
     """d^order u / d t^order (reference neurodiffeq.py:63-82)."""
     return safe_diff(u, t, order=order) if shape_check else unsafe_diff(u, t, order=order)

@@ -25,6 +25,7 @@ import torch.nn as nn
 
 from .conditions import BaseCondition
 from .engine import FusedProblem
+from ._compat import renamed_arguments
 from .losses import _losses, h1_rows
 from .generators import Generator1D, Generator2D, GeneratorSpherical, SamplerGenerator
 from .networks import FCNN
@@ -80,6 +81,7 @@ class BaseSolution:
             self._problem = FusedProblem(self.nets, self.conditions, None, self._n_coords, self._cfc)
         return self._problem
 
+    @renamed_arguments(as_type="to_numpy")                          # reference solvers.py:681
     def __call__(self, *coords, to_numpy=False, no_reshape=False):
         if isinstance(to_numpy, str):  # legacy `as_type`
             if to_numpy in ("tf", "torch"):
@@ -103,14 +105,11 @@ class BaseSolver:
 
     N_COORDS = None  # set by subclasses that know it a priori
 
+    @renamed_arguments(criterion="loss_fn")                          # reference solvers.py:113
     def __init__(self, diff_eqs, conditions, nets=None, train_generator=None, valid_generator=None,
                  analytic_solutions=None, optimizer=None, loss_fn=None, n_batches_train=1, n_batches_valid=4,
                  metrics=None, n_input_units=None, n_output_units=None, shuffle=None, batch_size=None,
-                 device=None, data_parallel=True, **legacy):
-        if "criterion" in legacy:
-            loss_fn = legacy.pop("criterion")
-        if legacy:
-            raise TypeError(f"unexpected keyword arguments {list(legacy)}")
+                 device=None, data_parallel=True):
         if shuffle:
             warnings.warn("param `shuffle` is deprecated and ignored; shuffling should be performed by generators",
                           FutureWarning)
@@ -464,6 +463,7 @@ class BaseSolver:
             "train_generator": self.generator["train"], "valid_generator": self.generator["valid"],
         }
 
+    @renamed_arguments(param_names="var_names")
     def get_internals(self, var_names=None, return_type="list"):
         available = self._get_internal_variables()
         if var_names == "all" or var_names is None:

@@ -199,3 +199,39 @@ def test_wrapping_generators():
         G.GeneratorND(grid=(4,), r_min=0.0, r_max=1.0, methods="sobol")
     with pytest.raises(ValueError):
         G.GeneratorND(grid=(4,), r_min=0.0, r_max=1.0, methods="uniform", stride=2)
+
+
+def test_deprecated_argument_names_behave_like_the_reference():
+    """reference tests/test_conditions.py:235-350 and _version_utils.py:21-48: old keyword names work with a
+    FutureWarning, both spellings at once are a KeyError, unknown bundle parameters a ValueError."""
+    from neurodiffeq_b200.conditions import IVP, BundleIVP, DirichletBVP, BundleDirichletBVP
+    from neurodiffeq_b200 import diff
+    with pytest.warns(FutureWarning):
+        c = IVP(0, x_0=1)
+    assert c.u_0 == 1
+    with pytest.warns(FutureWarning):
+        assert IVP(0, 1, x_0_prime=2).u_0_prime == 2
+    with pytest.raises(KeyError):
+        IVP(0, x_0=1, u_0=2)
+    with pytest.raises(KeyError):
+        IVP(0, x_0_prime=1, u_0_prime=2)
+    for bad in ("magic", "t0", "u1", "u1prime"):
+        with pytest.raises(ValueError):
+            BundleIVP(0.0, 1.0, 2.0, bundle_param_lookup={bad: 0})
+    for bad in ("magic", "u0", "t0", "u1", "t1"):
+        with pytest.raises(ValueError):
+            BundleDirichletBVP(0.0, 1.0, 2.0, 3.0, bundle_param_lookup={bad: 0})
+    with pytest.warns(FutureWarning):
+        BundleIVP(0.0, 1.0, bundle_conditions={"t_0": 0})
+    with pytest.warns(FutureWarning):
+        BundleDirichletBVP(0.0, 1.0, 2.0, 3.0, bundle_conditions={"t_0": 0})
+    with pytest.warns(FutureWarning):
+        b = DirichletBVP(t_0=0, t_1=1, x_0=2, x_1=3)
+    assert (b.u_0, b.u_1) == (2, 3)
+    with pytest.raises(KeyError):
+        DirichletBVP(t_0=0, u_0=0, x_0=0, t_1=0, x_1=0)
+    with pytest.raises(KeyError), pytest.warns(FutureWarning):       # x_0 renamed (warning), then x_1 clashes with u_1
+        DirichletBVP(t_0=0, x_0=0, t_1=0, x_1=0, u_1=0)
+    t = torch.linspace(0, 1, 5).reshape(-1, 1).requires_grad_(True)
+    with pytest.warns(FutureWarning):
+        assert torch.allclose(diff(x=t ** 2, t=t), 2 * t)
