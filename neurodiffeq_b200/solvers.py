@@ -182,6 +182,34 @@ class BaseSolver:
     def additional_loss(self, residual, funcs, coords):
         return 0.0
 
+    def _loss_value(self, residual, funcs, coords):
+        try:
+            return self._custom_loss(residual, funcs, coords) + self.additional_loss(residual, funcs, coords)
+        except TypeError as e:   # reference solvers.py:384-389
+            warnings.warn("You might need to update your code. Since v0.4.0; both `criterion` and `additional_loss` "
+                          "requires three inputs: `residual`, `funcs`, and `coords`. See documentation for more.",
+                          FutureWarning)
+            raise e
+
+    @property
+    def _batch_examples(self):
+        warnings.warn("`._batch_examples` has been deprecated in favor of `._batch`", FutureWarning)
+        return self._batch
+
+    def _update_train_history(self, value, metric_type):
+        self._update_history(value, metric_type, key="train")
+
+    def _update_valid_history(self, value, metric_type):
+        self._update_history(value, metric_type, key="valid")
+
+    def _generate_train_batch(self):
+        self._generate_batch("train")
+        return self._batch["train"]
+
+    def _generate_valid_batch(self):
+        self._generate_batch("valid")
+        return self._batch["valid"]
+
     def _set_loss_fn(self, criterion):
         # None / 'l2' / nn.MSELoss: the fused mean-squared residual (reference solvers.py:216-226, losses.py:10-12).
         # Any other callable (residual, funcs, coords) -> scalar is differentiated by autograd w.r.t. the residual matrix
@@ -304,7 +332,7 @@ class BaseSolver:
                     res = r.t().contiguous().requires_grad_(True)
                     u = u.requires_grad_(True)
                     funcs = _functions(fp.tp, u)
-                    loss = self._custom_loss(res, funcs, cols) + self.additional_loss(res, funcs, cols)
+                    loss = self._loss_value(res, funcs, cols)
                     loss.backward()
                     fp.residual_grad(coords, rbar=_grad_or_zeros(res).t().contiguous(), ubar=u.grad, sumsq_out=fp.sumsq,
                                      repack=False)
@@ -358,7 +386,7 @@ class BaseSolver:
                 res = r.t().contiguous().requires_grad_(key == "train")      # (N, n_eq) like torch.cat(residuals, 1)
                 u = u.requires_grad_(key == "train")                         # leaf: dL/du if the loss looks at the functions
                 funcs = _functions(fp.tp, u)
-                loss = self._custom_loss(res, funcs, cols) + self.additional_loss(res, funcs, cols)
+                loss = self._loss_value(res, funcs, cols)
                 if key == "train":
                     loss.backward()                                          # only to get dL/dr, dL/du on the tiny leaves
                     fp.residual_grad(coords, rbar=_grad_or_zeros(res).t().contiguous(), ubar=u.grad, sumsq_out=fp.sumsq,
