@@ -520,6 +520,12 @@ def _dispatch_function(name, args, kwargs):
         return g.unary("exp", g.mul(math.log(2.0), args[0]))
     if name == "sigmoid":
         return g.unary("rcp", g.add(1.0, g.unary("exp", g.neg(args[0]))))
+    if name in ("atan2", "arctan2"):
+        # half-angle form  atan2(y, x) = 2 atan(y / (sqrt(x^2 + y^2) + x)):  exact away from the non-positive x axis
+        # (where the reference's own coordinate conversions are singular for the angles too)
+        y, x = g.lift(args[0]), g.lift(args[1])
+        r = g.unary("sqrt", g.add(g.mul(x, x), g.mul(y, y)))
+        return g.mul(2.0, g.unary("atan", g.div(y, g.add(r, x))))
     if name == "cat" or name == "concatenate" or name == "stack":
         raise NotImplementedError("torch.cat of traced columns: only `condition.enforce(net, *coords)` may "
                                   "concatenate coordinates (that is where the network input is recorded)")

@@ -244,3 +244,26 @@ def bundle_eq_wrapper(workload):
         return workload.diff_eqs(*head, *(variables[i] for i in idx))
 
     return wrapped
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# operators.py golden cases: closed-form fields of three coordinates, usable on tensors and on traced symbols
+# ----------------------------------------------------------------------------------------------------------------------
+OPERATOR_NAMES = ("grad", "div", "curl", "laplacian", "vector_laplacian", "spherical_curl", "spherical_grad", "spherical_div",
+                  "spherical_laplacian", "spherical_vector_laplacian", "spherical_to_cartesian", "cartesian_to_spherical",
+                  "cylindrical_grad", "cylindrical_div", "cylindrical_curl", "cylindrical_laplacian",
+                  "cylindrical_vector_laplacian", "cylindrical_to_cartesian", "cartesian_to_cylindrical")
+_SCALAR_OPERATORS = ("grad", "laplacian", "spherical_grad", "spherical_laplacian", "cylindrical_grad", "cylindrical_laplacian")
+
+
+def operator_fields(a, b, d):
+    """three smooth closed-form fields of the coordinates (a, b, d)"""
+    return (torch.sin(a) * b + d ** 2 * torch.cos(b), a * b * d + torch.exp(-a) * torch.sin(d), torch.cos(a * d) + b ** 2)
+
+
+def operator_arguments(name, coords):
+    """positional arguments of operator ``name`` for the golden case: (field(s)..., *coords) or just the coordinates"""
+    if name.endswith("_to_cartesian") or name.startswith("cartesian_to"):
+        return tuple(coords)
+    f = operator_fields(*coords)
+    return (f[0], *coords) if name in _SCALAR_OPERATORS else (*f, *coords)
