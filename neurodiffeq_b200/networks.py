@@ -47,3 +47,70 @@ class FCNN(nn.Module):
 
     def forward(self, t):
         return self.NN(t)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The remaining modules of the reference's networks.py.  They are ordinary torch modules (usable in eager code, same
+# semantics as the reference); the fused engine has no jet rule for them yet and says so when a solver is built with one.
+# ----------------------------------------------------------------------------------------------------------------------
+class Resnet(nn.Module):
+    """``skip_connection(t) + residual(t)``: a bias-free Linear from input to output beside an FCNN (networks.py:73-106)."""
+
+    def __init__(self, n_input_units=1, n_output_units=1, n_hidden_units=None, n_hidden_layers=None, actv=nn.Tanh,
+                 hidden_units=(32, 32)):
+        super().__init__()
+        self.residual = FCNN(n_input_units=n_input_units, n_output_units=n_output_units, n_hidden_units=n_hidden_units,
+                             n_hidden_layers=n_hidden_layers, actv=actv, hidden_units=hidden_units)
+        self.skip_connection = nn.Linear(n_input_units, n_output_units, bias=False)
+
+    def forward(self, t):
+        return self.skip_connection(t) + self.residual(t)
+
+
+class MonomialNN(nn.Module):
+    """Feature map ``x -> [x**d for d in degrees]`` concatenated along dim 1 (networks.py:109-139)."""
+
+    def __init__(self, degrees):
+        super().__init__()
+        if isinstance(degrees, int):
+            degrees = list(range(1, degrees + 1))
+        self.degrees = tuple(degrees)
+        if len(self.degrees) == 0:
+            raise ValueError("No degrees used, check `degrees` argument again")
+        if 0 in self.degrees:
+            warn("One of the degrees is 0 which might introduce redundant features")
+        if len(set(self.degrees)) < len(self.degrees):
+            warn(f"Duplicate degrees found: {self.degrees}")
+
+    def forward(self, x):
+        return torch.cat([x ** d for d in self.degrees], dim=1)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(degrees={self.degrees})"
+
+    __str__ = __repr__
+
+
+class Swish(nn.Module):
+    """``x * sigmoid(beta * x)`` with an optionally trainable ``beta`` (networks.py:155-174)."""
+
+    def __init__(self, beta=1.0, trainable=False):
+        super().__init__()
+        self.trainable = trainable
+        self.beta = nn.Parameter(torch.tensor(float(beta))) if trainable else float(beta)
+
+    def forward(self, x):
+        return x * torch.sigmoid(self.beta * x)
+
+
+class APTx(nn.Module):
+    """``(alpha + tanh(beta * x)) * gamma * x`` with optionally trainable scalars (networks.py:177-208)."""
+
+    def __init__(self, alpha=1.0, beta=1.0, gamma=0.5, trainable=False):
+        super().__init__()
+        self.trainable = trainable
+        wrap = (lambda v: nn.Parameter(torch.tensor(float(v)))) if trainable else float
+        self.alpha, self.beta, self.gamma = wrap(alpha), wrap(beta), wrap(gamma)
+
+    def forward(self, x):
+        return (self.alpha + torch.tanh(self.beta * x)) * self.gamma * x

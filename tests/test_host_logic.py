@@ -235,3 +235,33 @@ def test_deprecated_argument_names_behave_like_the_reference():
     t = torch.linspace(0, 1, 5).reshape(-1, 1).requires_grad_(True)
     with pytest.warns(FutureWarning):
         assert torch.allclose(diff(x=t ** 2, t=t), 2 * t)
+
+
+def test_network_modules_of_the_reference():
+    """Resnet / MonomialNN / Swish / APTx (reference networks.py:73-208, tests/test_networks.py): eager semantics; a fused
+    solver refuses them with a clear NotImplementedError instead of computing something else."""
+    import torch.nn as nn
+    from neurodiffeq_b200.networks import FCNN, Resnet, MonomialNN, Swish, APTx
+    from neurodiffeq_b200.conditions import NoCondition
+    from neurodiffeq_b200.tracing import TracedProblem
+    from neurodiffeq_b200 import diff
+    x = torch.linspace(-1, 1, 7).reshape(-1, 1)
+    r = Resnet(1, 2, hidden_units=(8,))
+    assert torch.allclose(r(x), r.skip_connection(x) + r.residual(x)) and r(x).shape == (7, 2)
+    assert r.skip_connection.bias is None
+    m = MonomialNN(3)
+    assert m.degrees == (1, 2, 3) and torch.allclose(m(x), torch.cat([x, x ** 2, x ** 3], 1))
+    assert MonomialNN([2, 4])(x).shape == (7, 2) and "degrees=(2, 4)" in repr(MonomialNN([2, 4]))
+    with pytest.raises(ValueError):
+        MonomialNN([])
+    with pytest.warns(UserWarning):
+        MonomialNN([0, 1])
+    with pytest.warns(UserWarning):
+        MonomialNN([1, 1])
+    assert torch.allclose(Swish(2.0)(x), x * torch.sigmoid(2.0 * x))
+    assert len(list(Swish(trainable=True).parameters())) == 1 and len(list(Swish().parameters())) == 0
+    assert torch.allclose(APTx(1.0, 2.0, 0.5)(x), (1.0 + torch.tanh(2.0 * x)) * 0.5 * x)
+    assert len(list(APTx(trainable=True).parameters())) == 3
+    for net in (Resnet(1, 1), FCNN(1, 1, actv=Swish), nn.Sequential(MonomialNN(2), nn.Linear(2, 1))):
+        with pytest.raises(NotImplementedError):
+            TracedProblem([net], [NoCondition()], lambda u, t: [diff(u, t)], 1)
