@@ -261,7 +261,6 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
         const int ns = pick_stages(fixed, pl.chunks_bwd, pl.ntc == 128 ? 2 : 1);
         if (ns < 0) return fail(-2, "backward kernel does not fit in shared memory");
         pl.resident_bwd = ns >= pl.chunks_bwd ? 1 : 0;
-        pl.chunks_bwd = pl.chunks_bwd;   // (kept)
         int o = 0;
         pl.k2_g0 = o; o += jet_bytes;
         pl.k2_g1 = o; o += jet_bytes;

@@ -170,17 +170,10 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-// sum over the 8 point-group lanes of a warp (lane bits 0..2)
-__device__ __forceinline__ float pg_sum(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    return v;
-}
 
 // Reduce-scatter over the 8 point-group lanes (recursive halving): every thread contributes 8 (or 4) partial sums, lane l
 // of each 8-lane group returns the total of value l (value l >> 1 for the 4-value form, in both lanes of a pair):
-// 7 (4) shuffles instead of 24 (12) for all-reduce style pg_sum calls.
+// 7 (4) shuffles instead of the 24 (12) of one butterfly all-reduce per value.
 __device__ __forceinline__ float pg_reduce_scatter8(const float (&v)[8], int pg_lane) {
     const bool b2 = pg_lane & 4, b1 = pg_lane & 2, b0 = pg_lane & 1;
     float w[4], x[2];
