@@ -53,64 +53,74 @@ class FCNN(nn.Module):
 # The remaining modules of the reference's networks.py.  They are ordinary torch modules (usable in eager code, same
 # semantics as the reference); the fused engine has no jet rule for them yet and says so when a solver is built with one.
 # ----------------------------------------------------------------------------------------------------------------------
+def _scalar(value, trainable):
+    """a python float, or a 0-dim Parameter when the activation's scalars are to be learned"""
+    value = float(value)
+    return nn.Parameter(torch.tensor(value)) if trainable else value
+
+
 class Resnet(nn.Module):
-    """``skip_connection(t) + residual(t)``: a bias-free Linear from input to output beside an FCNN (networks.py:73-106)."""
+    """FCNN plus a bias-free linear shortcut from the inputs to the outputs (reference networks.py:73-106); the
+    sub-modules keep the reference's names ``residual`` and ``skip_connection`` so that state dicts are interchangeable."""
 
     def __init__(self, n_input_units=1, n_output_units=1, n_hidden_units=None, n_hidden_layers=None, actv=nn.Tanh,
                  hidden_units=(32, 32)):
         super().__init__()
-        self.residual = FCNN(n_input_units=n_input_units, n_output_units=n_output_units, n_hidden_units=n_hidden_units,
-                             n_hidden_layers=n_hidden_layers, actv=actv, hidden_units=hidden_units)
+        body = dict(n_hidden_units=n_hidden_units, n_hidden_layers=n_hidden_layers, actv=actv, hidden_units=hidden_units)
+        self.residual = FCNN(n_input_units, n_output_units, **body)
         self.skip_connection = nn.Linear(n_input_units, n_output_units, bias=False)
 
     def forward(self, t):
-        return self.skip_connection(t) + self.residual(t)
+        shortcut = self.skip_connection(t)
+        return shortcut + self.residual(t)
 
 
 class MonomialNN(nn.Module):
-    """Feature map ``x -> [x**d for d in degrees]`` concatenated along dim 1 (networks.py:109-139)."""
+    """Parameter-free feature map: the columns of ``x`` raised to each of ``degrees`` (an int n means 1..n), side by
+    side -> ``(n_samples, n_inputs * len(degrees))`` (reference networks.py:109-139)."""
 
     def __init__(self, degrees):
         super().__init__()
-        if isinstance(degrees, int):
-            degrees = list(range(1, degrees + 1))
-        self.degrees = tuple(degrees)
-        if len(self.degrees) == 0:
+        powers = tuple(range(1, degrees + 1)) if isinstance(degrees, int) else tuple(degrees)
+        if not powers:
             raise ValueError("No degrees used, check `degrees` argument again")
-        if 0 in self.degrees:
+        if any(p == 0 for p in powers):
             warn("One of the degrees is 0 which might introduce redundant features")
-        if len(set(self.degrees)) < len(self.degrees):
-            warn(f"Duplicate degrees found: {self.degrees}")
+        if len(powers) != len(set(powers)):
+            warn(f"Duplicate degrees found: {powers}")
+        self.degrees = powers
 
     def forward(self, x):
-        return torch.cat([x ** d for d in self.degrees], dim=1)
+        return torch.cat(tuple(torch.pow(x, p) for p in self.degrees), dim=1)
+
+    def extra_repr(self):
+        return f"degrees={self.degrees}"
 
     def __repr__(self):
-        return f"{self.__class__.__name__}(degrees={self.degrees})"
-
-    __str__ = __repr__
+        return f"{type(self).__name__}({self.extra_repr()})"
 
 
 class Swish(nn.Module):
-    """``x * sigmoid(beta * x)`` with an optionally trainable ``beta`` (networks.py:155-174)."""
+    """swish(x) = x / (1 + exp(-beta x)); ``beta`` may be trainable (reference networks.py:155-174)."""
 
     def __init__(self, beta=1.0, trainable=False):
         super().__init__()
         self.trainable = trainable
-        self.beta = nn.Parameter(torch.tensor(float(beta))) if trainable else float(beta)
+        self.beta = _scalar(beta, trainable)
 
     def forward(self, x):
-        return x * torch.sigmoid(self.beta * x)
+        gate = torch.sigmoid(x * self.beta)
+        return gate * x
 
 
 class APTx(nn.Module):
-    """``(alpha + tanh(beta * x)) * gamma * x`` with optionally trainable scalars (networks.py:177-208)."""
+    """APTx(x) = (alpha + tanh(beta x)) gamma x, a cheaper look-alike of MISH; the three scalars may be trainable
+    (reference networks.py:177-208)."""
 
     def __init__(self, alpha=1.0, beta=1.0, gamma=0.5, trainable=False):
         super().__init__()
         self.trainable = trainable
-        wrap = (lambda v: nn.Parameter(torch.tensor(float(v)))) if trainable else float
-        self.alpha, self.beta, self.gamma = wrap(alpha), wrap(beta), wrap(gamma)
+        self.alpha, self.beta, self.gamma = (_scalar(v, trainable) for v in (alpha, beta, gamma))
 
     def forward(self, x):
-        return (self.alpha + torch.tanh(self.beta * x)) * self.gamma * x
+        return self.gamma * x * (torch.tanh(x * self.beta) + self.alpha)
