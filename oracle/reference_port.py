@@ -12,7 +12,6 @@ which ``tests/test_oracle.py`` compares this file against (residual, loss and ev
 
 Each function cites the reference lines it follows (paths relative to /root/reference).
 """
-import math
 import types
 
 import torch

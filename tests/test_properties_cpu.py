@@ -4,7 +4,6 @@ tests/test_conditions.py:142-583), including the Neumann ends that evaluate the 
 calculus identities (tests/test_operators_identities.py:57-143); `diff` of closed forms (tests/test_neurodiffeq.py:87-96).
 The GPU suite repeats the core of this through the CUDA kernels at fp32 tolerances (tests/test_properties_gpu.py)."""
 import numpy as np
-import pytest
 import torch
 
 from cpu_engine import CpuFusedProblem
