@@ -240,3 +240,26 @@ def test_flat_adam_equals_torch_adam_cpu():
         np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-13)
     s_flat.optimizer.param_groups[0]["lr"] = 5e-4      # schedulers / callbacks edit param_groups as with any optimizer
     s_flat.fit(1, tqdm_file=None)
+
+
+def test_training_converges_to_the_analytic_solution_cpu():
+    """End to end, like the reference's tests/test_ode.py: u' = -u, u(0) = 1 on [0, 2] trained with Adam reaches the
+    analytic solution exp(-t) (loose bound; the point is that value, residual, gradient, optimizer and best-network
+    bookkeeping work together)."""
+    import neurodiffeq_b200.solvers as Sv
+    from neurodiffeq_b200 import diff
+    from neurodiffeq_b200.conditions import IVP
+    from neurodiffeq_b200.generators import Generator1D
+    from neurodiffeq_b200.networks import FCNN
+    torch.manual_seed(0)
+    net = FCNN(1, 1, hidden_units=(16, 16))
+    solver = Sv.Solver1D(lambda u, t: [diff(u, t) + u], [IVP(0.0, 1.0)], t_min=0.0, t_max=2.0, nets=[net],
+                         train_generator=Generator1D(48, 0.0, 2.0, "equally-spaced-noisy"),
+                         valid_generator=Generator1D(32, 0.0, 2.0, "equally-spaced"), n_batches_valid=1,
+                         optimizer=torch.optim.Adam(net.parameters(), lr=5e-3))
+    solver.fit(400, tqdm_file=None)
+    ts = np.linspace(0.0, 2.0, 41)
+    u = solver.get_solution(best=True)(ts, to_numpy=True)
+    assert solver.metrics_history["valid_loss"][-1] < 1e-3 * solver.metrics_history["valid_loss"][0]
+    assert np.abs(u - np.exp(-ts)).max() < 2e-2
+    assert solver.lowest_loss == min(solver.metrics_history["valid_loss"])
