@@ -70,3 +70,53 @@ def test_shard_bounds_tile_the_batch():
             assert all(a[1] == b[0] for a, b in zip(edges[:-1], edges[1:]))
             sizes = [hi - lo for lo, hi in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _solver_worker(rank, world, port, key, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_default_dtype(torch.float64)
+    import neurodiffeq_b200.solvers as S
+    from cpu_engine import CpuFusedProblem
+    from test_solvers_gpu import make_solver
+    S.FusedProblem = CpuFusedProblem                    # the stand-in engine; the data-parallel logic is the product's
+    wl, solver, nets, coords_np = make_solver(key, 150)  # same seed on every rank -> same parameters, same batch
+    assert solver._dist is not None
+    solver.fit(3, tqdm_file=None)
+    from helpers import get_params
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), train=np.array(solver.metrics_history["train_loss"]),
+             valid=np.array(solver.metrics_history["valid_loss"]), theta=np.concatenate([p.reshape(-1) for p in get_params(nets)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("key", ["c2", "x4"])
+def test_solver_fit_on_two_ranks_equals_one_process(key, tmp_path, monkeypatch):
+    """Solver.fit under torch.distributed: every rank samples the same batch, keeps its slice, the flat
+    [grad | sum r^2] buffer is all-reduced once per epoch phase and the replicated Adam stays in lock-step -- losses and
+    parameters equal the single-process run, and the ranks agree bit for bit."""
+    world = 2
+    port = 31000 + (os.getpid() % 2000)
+    mp.start_processes(_solver_worker, args=(world, port, key, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    r0, r1 = np.load(os.path.join(str(tmp_path), "rank0.npz")), np.load(os.path.join(str(tmp_path), "rank1.npz"))
+    assert np.array_equal(r0["theta"], r1["theta"]) and np.array_equal(r0["train"], r1["train"])
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import neurodiffeq_b200.solvers as S
+    from cpu_engine import CpuFusedProblem
+    from test_solvers_gpu import make_solver
+    from helpers import get_params
+    monkeypatch.setattr(S, "FusedProblem", CpuFusedProblem)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        wl, solver, nets, _ = make_solver(key, 150)
+        solver.fit(3, tqdm_file=None)
+    finally:
+        torch.set_default_dtype(old)
+    np.testing.assert_allclose(r0["train"], solver.metrics_history["train_loss"], rtol=1e-6)
+    np.testing.assert_allclose(r0["valid"], solver.metrics_history["valid_loss"], rtol=1e-6)
+    theta = np.concatenate([p.reshape(-1) for p in get_params(nets)])
+    np.testing.assert_allclose(r0["theta"], theta, rtol=1e-8, atol=1e-11)
