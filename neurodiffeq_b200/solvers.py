@@ -182,6 +182,12 @@ class BaseSolver:
     def additional_loss(self, residual, funcs, coords):
         return 0.0
 
+    def _batch_share(self, residual):
+        """Under data parallelism a custom loss sees this rank's slice of the batch; losses are means over the batch
+        points (every loss of the reference is), so the slice contributes n_local / n_global of the batch loss -- and of
+        its gradient; the all-reduce then SUMS the shares.  1 on a single rank."""
+        return 1.0 if self._dist is None else residual.shape[0] / float(self._n_global)
+
     def _loss_value(self, residual, funcs, coords):
         try:
             return self._custom_loss(residual, funcs, coords) + self.additional_loss(residual, funcs, coords)
@@ -332,15 +338,15 @@ class BaseSolver:
                     res = r.t().contiguous().requires_grad_(True)
                     u = u.requires_grad_(True)
                     funcs = _functions(fp.tp, u)
-                    loss = self._loss_value(res, funcs, cols)
+                    loss = self._loss_value(res, funcs, cols) * self._batch_share(res)
                     loss.backward()
                     fp.residual_grad(coords, rbar=_grad_or_zeros(res).t().contiguous(), ubar=u.grad, sumsq_out=fp.sumsq,
                                      repack=False)
                     loss = loss.detach().reshape(()).to(fp.sumsq.dtype)
                     if self._dist is not None:
                         fp.sumsq.copy_(loss.reshape(1))
-                        self._dist.all_reduce(fp.gradbuf)
-                        loss = (fp.sumsq / self._dist.get_world_size()).reshape(()).clone()
+                        self._dist.all_reduce(fp.gradbuf)    # the shares add up to the loss of the whole batch
+                        loss = fp.sumsq.reshape(()).clone()
                 self._eval_metrics(coords, metric_values)    # inside the closure, like the reference (:376-378)
                 last["loss"] = loss
                 return loss
@@ -386,7 +392,7 @@ class BaseSolver:
                 res = r.t().contiguous().requires_grad_(key == "train")      # (N, n_eq) like torch.cat(residuals, 1)
                 u = u.requires_grad_(key == "train")                         # leaf: dL/du if the loss looks at the functions
                 funcs = _functions(fp.tp, u)
-                loss = self._loss_value(res, funcs, cols)
+                loss = self._loss_value(res, funcs, cols) * self._batch_share(res)
                 if key == "train":
                     loss.backward()                                          # only to get dL/dr, dL/du on the tiny leaves
                     fp.residual_grad(coords, rbar=_grad_or_zeros(res).t().contiguous(), ubar=u.grad, sumsq_out=fp.sumsq,
@@ -400,8 +406,6 @@ class BaseSolver:
             else:
                 self._dist.all_reduce(fp.sumsq)
             loss_acc = fp.sumsq.clone()
-            if self._custom_loss is not None:
-                loss_acc /= self._dist.get_world_size()
         epoch_loss = float(loss_acc.item()) / n_b        # mean of the batch losses (reference solvers.py:410)
         self._update_history(epoch_loss, "loss", key)
         if key == "valid" or self.n_batches["valid"] == 0:

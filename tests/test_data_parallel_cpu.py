@@ -72,7 +72,11 @@ def test_shard_bounds_tile_the_batch():
             assert max(sizes) - min(sizes) <= 1
 
 
-def _solver_worker(rank, world, port, key, out_dir):
+def _funcs_loss(residual, funcs, coords):     # module level: picklable for the spawned ranks
+    return residual.abs().mean() + 0.2 * (funcs[0] ** 2).mean()
+
+
+def _solver_worker(rank, world, port, key, out_dir, loss_fn=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -83,7 +87,8 @@ def _solver_worker(rank, world, port, key, out_dir):
     from cpu_engine import CpuFusedProblem
     from test_solvers_gpu import make_solver
     S.FusedProblem = CpuFusedProblem                    # the stand-in engine; the data-parallel logic is the product's
-    wl, solver, nets, coords_np = make_solver(key, 150)  # same seed on every rank -> same parameters, same batch
+    kw = {} if loss_fn is None else dict(loss_fn=loss_fn)
+    wl, solver, nets, coords_np = make_solver(key, 150, **kw)  # same seed on every rank -> same parameters, same batch
     assert solver._dist is not None
     solver.fit(3, tqdm_file=None)
     from helpers import get_params
@@ -93,14 +98,15 @@ def _solver_worker(rank, world, port, key, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("key", ["c2", "x4"])
-def test_solver_fit_on_two_ranks_equals_one_process(key, tmp_path, monkeypatch):
+@pytest.mark.parametrize("key,loss_fn", [("c2", None), ("x4", None), ("c2", "l1"), ("c2", _funcs_loss)])
+def test_solver_fit_on_two_ranks_equals_one_process(key, loss_fn, tmp_path, monkeypatch):
     """Solver.fit under torch.distributed: every rank samples the same batch, keeps its slice, the flat
     [grad | sum r^2] buffer is all-reduced once per epoch phase and the replicated Adam stays in lock-step -- losses and
     parameters equal the single-process run, and the ranks agree bit for bit."""
     world = 2
     port = 31000 + (os.getpid() % 2000)
-    mp.start_processes(_solver_worker, args=(world, port, key, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    mp.start_processes(_solver_worker, args=(world, port, key, str(tmp_path), loss_fn), nprocs=world, join=True,
+                       start_method="spawn")
     r0, r1 = np.load(os.path.join(str(tmp_path), "rank0.npz")), np.load(os.path.join(str(tmp_path), "rank1.npz"))
     assert np.array_equal(r0["theta"], r1["theta"]) and np.array_equal(r0["train"], r1["train"])
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -112,7 +118,7 @@ def test_solver_fit_on_two_ranks_equals_one_process(key, tmp_path, monkeypatch):
     old = torch.get_default_dtype()
     torch.set_default_dtype(torch.float64)
     try:
-        wl, solver, nets, _ = make_solver(key, 150)
+        wl, solver, nets, _ = make_solver(key, 150, **({} if loss_fn is None else dict(loss_fn=loss_fn)))
         solver.fit(3, tqdm_file=None)
     finally:
         torch.set_default_dtype(old)
