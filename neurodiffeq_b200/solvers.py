@@ -356,6 +356,17 @@ class BaseSolver:
         self._update_history(epoch_loss / n_b, "loss", key)
         if self.n_batches["valid"] == 0:
             self._update_best(key)
+        self._record_metrics(metric_values, n_b, key)
+
+    def _record_metrics(self, metric_values, n_b, key):
+        """Metrics are evaluated on this rank's slice; under data parallelism the ranks average them (one small
+        all-reduce) so that every rank keeps the same history."""
+        if self.metrics_fn and self._dist is not None:
+            names = list(self.metrics_fn)
+            buf = torch.tensor([metric_values[n] for n in names], dtype=torch.float64, device=self.device)
+            self._dist.all_reduce(buf)
+            for n, v in zip(names, (buf / self._dist.get_world_size()).tolist()):
+                metric_values[n] = v
         for name in self.metrics_fn:
             self._update_history(metric_values[name] / n_b, name, key)
 
@@ -412,8 +423,7 @@ class BaseSolver:
             self._update_best(key)
         if key == "train":
             self._do_optimizer_step()
-        for name in self.metrics_fn:
-            self._update_history(metric_values[name] / n_b, name, key)
+        self._record_metrics(metric_values, n_b, key)
 
     def run_train_epoch(self):
         self._run_epoch("train")

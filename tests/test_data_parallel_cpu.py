@@ -72,6 +72,10 @@ def test_shard_bounds_tile_the_batch():
             assert max(sizes) - min(sizes) <= 1
 
 
+def _mean_u(u, x, y):
+    return u.mean()
+
+
 def _funcs_loss(residual, funcs, coords):     # module level: picklable for the spawned ranks
     return residual.abs().mean() + 0.2 * (funcs[0] ** 2).mean()
 
@@ -88,12 +92,15 @@ def _solver_worker(rank, world, port, key, out_dir, loss_fn=None):
     from test_solvers_gpu import make_solver
     S.FusedProblem = CpuFusedProblem                    # the stand-in engine; the data-parallel logic is the product's
     kw = {} if loss_fn is None else dict(loss_fn=loss_fn)
+    if key == "c2":
+        kw["metrics"] = {"mean_u": _mean_u}
     wl, solver, nets, coords_np = make_solver(key, 150, **kw)  # same seed on every rank -> same parameters, same batch
     assert solver._dist is not None
     solver.fit(3, tqdm_file=None)
     from helpers import get_params
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), train=np.array(solver.metrics_history["train_loss"]),
-             valid=np.array(solver.metrics_history["valid_loss"]), theta=np.concatenate([p.reshape(-1) for p in get_params(nets)]))
+             valid=np.array(solver.metrics_history["valid_loss"]),
+             metric=np.array(solver.metrics_history.get("train__mean_u", [])), theta=np.concatenate([p.reshape(-1) for p in get_params(nets)]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -109,6 +116,7 @@ def test_solver_fit_on_two_ranks_equals_one_process(key, loss_fn, tmp_path, monk
                        start_method="spawn")
     r0, r1 = np.load(os.path.join(str(tmp_path), "rank0.npz")), np.load(os.path.join(str(tmp_path), "rank1.npz"))
     assert np.array_equal(r0["theta"], r1["theta"]) and np.array_equal(r0["train"], r1["train"])
+    assert np.array_equal(r0["metric"], r1["metric"]) and (key != "c2" or len(r0["metric"]) == 3)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import neurodiffeq_b200.solvers as S
     from cpu_engine import CpuFusedProblem
