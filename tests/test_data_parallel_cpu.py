@@ -134,3 +134,44 @@ def test_solver_fit_on_two_ranks_equals_one_process(key, loss_fn, tmp_path, monk
     np.testing.assert_allclose(r0["valid"], solver.metrics_history["valid_loss"], rtol=1e-6)
     theta = np.concatenate([p.reshape(-1) for p in get_params(nets)])
     np.testing.assert_allclose(r0["theta"], theta, rtol=1e-8, atol=1e-11)
+
+
+def _lbfgs_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    if world > 1:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_default_dtype(torch.float64)
+    import workloads
+    import neurodiffeq_b200.solvers as S
+    from cpu_engine import CpuFusedProblem
+    from helpers import product_namespace, get_params
+    from neurodiffeq_b200.generators import PredefinedGenerator
+    S.FusedProblem = CpuFusedProblem
+    wl = workloads.build(product_namespace(), "x6")
+    torch.manual_seed(0)
+    nets = wl.make_nets()
+    gen = PredefinedGenerator(*workloads.sample_coords(wl, 90, seed=21))
+    opt = torch.optim.LBFGS([p for m in nets for p in m.parameters()], lr=0.5, max_iter=3, history_size=4)
+    solver = S.Solver1D(wl.diff_eqs, wl.make_conditions(), nets=nets, train_generator=gen, valid_generator=gen,
+                        n_batches_valid=1, optimizer=opt)
+    solver.fit(2, tqdm_file=None)
+    np.savez(os.path.join(out_dir, f"lbfgs_w{world}_r{rank}.npz"), train=np.array(solver.metrics_history["train_loss"]),
+             theta=np.concatenate([p.reshape(-1) for p in get_params(nets)]))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_lbfgs_closure_mode_on_two_ranks(tmp_path):
+    """Every closure evaluation all-reduces [grad | loss]; LBFGS then takes identical decisions on every rank."""
+    port = 33000 + (os.getpid() % 2000)
+    mp.start_processes(_lbfgs_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True, start_method="spawn")
+    mp.start_processes(_lbfgs_worker, args=(1, port + 1, str(tmp_path)), nprocs=1, join=True, start_method="spawn")
+    a, b = np.load(os.path.join(str(tmp_path), "lbfgs_w2_r0.npz")), np.load(os.path.join(str(tmp_path), "lbfgs_w2_r1.npz"))
+    one = np.load(os.path.join(str(tmp_path), "lbfgs_w1_r0.npz"))
+    assert np.array_equal(a["theta"], b["theta"])
+    np.testing.assert_allclose(a["train"], one["train"], rtol=1e-6)
+    np.testing.assert_allclose(a["theta"], one["theta"], rtol=1e-6, atol=1e-9)
