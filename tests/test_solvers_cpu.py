@@ -263,3 +263,28 @@ def test_training_converges_to_the_analytic_solution_cpu():
     assert solver.metrics_history["valid_loss"][-1] < 1e-3 * solver.metrics_history["valid_loss"][0]
     assert np.abs(u - np.exp(-ts)).max() < 2e-2
     assert solver.lowest_loss == min(solver.metrics_history["valid_loss"])
+
+
+def test_bundle_and_spherical_solutions_cpu():
+    """BundleSolution1D takes (t, *bundle parameters); SolutionSpherical takes (r, theta, phi); both reshape to the
+    first argument's shape and honour the conditions (reference solvers.py:977-1013, 1184-1187)."""
+    wl, solver, nets, coords_np = make_solver("c5", 64)
+    solver.fit(1, tqdm_file=None)
+    sol = solver.get_solution(best=False)
+    t0 = np.zeros((3, 4))
+    zeta, omega = np.full((3, 4), 0.2), np.full((3, 4), 1.0)
+    u0, v0 = np.linspace(-1, 1, 12).reshape(3, 4), np.linspace(1, -1, 12).reshape(3, 4)
+    u, v = sol(t0, zeta, omega, u0, v0, to_numpy=True)
+    assert u.shape == (3, 4) and v.shape == (3, 4)
+    np.testing.assert_allclose(u, u0, atol=1e-7)                      # BundleIVP: u(t0) = u_0 taken per point
+    np.testing.assert_allclose(v, v0, atol=1e-7)
+    wl, solver, nets, coords_np = make_solver("c4", 48)
+    solver.fit(1, tqdm_file=None)
+    r = np.full(5, 0.1)
+    th, ph = np.linspace(0.3, 2.5, 5), np.linspace(0.1, 6.0, 5)
+    inner = solver.get_solution(best=True)(r, th, ph, to_numpy=True)
+    assert inner.shape == (5,) and np.allclose(inner, inner[0])       # constant Dirichlet value on the inner shell
+    res = solver.get_residuals(r + 1.0, th, ph, to_numpy=True)
+    assert res.shape == (5,) and np.isfinite(res).all()
+    internals = solver.get_internals(["nets", "conditions"], return_type="dict")
+    assert set(internals) == {"nets", "conditions"}
