@@ -17,7 +17,11 @@ import torch
 
 
 class FlatAdam(torch.optim.Optimizer):
-    def __init__(self, theta, grad, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    """``capturable=True`` keeps the step counter, the learning rate and the bias corrections in device tensors, so that
+    :meth:`step` is a fixed sequence of device operations (no host scalars that change from step to step) and can be
+    recorded into the CUDA graph that already holds K0..K2b: a whole training step then replays as one graph."""
+
+    def __init__(self, theta, grad, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
         if theta.dim() != 1 or grad.shape != theta.shape:
             raise ValueError("FlatAdam expects the flat parameter buffer and its flat gradient buffer")
         if not 0.0 <= lr or not 0.0 <= eps or not (0.0 <= betas[0] < 1.0 and 0.0 <= betas[1] < 1.0):
@@ -28,6 +32,32 @@ class FlatAdam(torch.optim.Optimizer):
         self._m = torch.zeros_like(theta)
         self._v = torch.zeros_like(theta)
         self._t = 0
+        self.capturable = capturable
+        if capturable:
+            f64 = dict(dtype=torch.float64, device=theta.device)
+            self._t_dev = torch.zeros((), **f64)
+            self._lr_dev = torch.tensor(float(lr), **f64)
+            self._lr_host = float(lr)
+
+    def sync_hyperparameters(self):
+        """Capturable mode: push a learning rate edited through ``param_groups`` (schedulers, callbacks) to the device.
+        Call outside the captured region, before a replay."""
+        lr = float(self.param_groups[0]["lr"])
+        if self.capturable and lr != self._lr_host:
+            self._lr_dev.fill_(lr)
+            self._lr_host = lr
+
+    def _step_on_device(self):
+        b1, b2 = self.param_groups[0]["betas"]
+        eps = self.param_groups[0]["eps"]
+        g = self._grad
+        self._t_dev.add_(1.0)
+        self._m.mul_(b1).add_(g, alpha=1.0 - b1)
+        self._v.mul_(b2).addcmul_(g, g, value=1.0 - b2)
+        bc1 = 1.0 - torch.pow(b1, self._t_dev)                     # 0-dim device tensors
+        bc2 = 1.0 - torch.pow(b2, self._t_dev)
+        denom = (self._v.sqrt() / bc2.sqrt().to(self._v.dtype)).add_(eps)
+        self._theta.sub_((self._m / denom) * (self._lr_dev / bc1).to(self._theta.dtype))
 
     @classmethod
     def for_solver(cls, solver, **kw):
@@ -39,6 +69,11 @@ class FlatAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        if self.capturable:
+            self.sync_hyperparameters()
+            self._step_on_device()
+            self._t += 1
+            return loss
         group = self.param_groups[0]
         lr, (b1, b2), eps = group["lr"], group["betas"], group["eps"]
         self._t += 1

@@ -223,8 +223,10 @@ def test_overridden_additional_loss_cpu():
         np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-11)
 
 
-def test_flat_adam_equals_torch_adam_cpu():
-    """optim.FlatAdam on the engine's flat buffers takes the same steps as torch.optim.Adam on the parameter views."""
+@pytest.mark.parametrize("capturable", [False, True])
+def test_flat_adam_equals_torch_adam_cpu(capturable):
+    """optim.FlatAdam on the engine's flat buffers takes the same steps as torch.optim.Adam on the parameter views; the
+    capturable variant keeps step count / learning rate / bias corrections in device tensors (graph-recordable)."""
     from neurodiffeq_b200.optim import FlatAdam
     key, n, epochs = "c2", 50, 6
     wl, s_ref, nets_ref, coords_np = make_solver(key, n)
@@ -233,13 +235,16 @@ def test_flat_adam_equals_torch_adam_cpu():
     wl, s_flat, nets_flat, _ = make_solver(key, n)
     from helpers import set_params
     set_params(nets_flat, p0)
-    s_flat.optimizer = FlatAdam.for_solver(s_flat, lr=1e-3)
+    s_flat.optimizer = FlatAdam.for_solver(s_flat, lr=1e-3, capturable=capturable)
     s_flat.fit(epochs, tqdm_file=None)
     np.testing.assert_allclose(s_flat.metrics_history["train_loss"], s_ref.metrics_history["train_loss"], rtol=1e-10)
     for a, b in zip(get_params(nets_flat), get_params(nets_ref)):
         np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-13)
-    s_flat.optimizer.param_groups[0]["lr"] = 5e-4      # schedulers / callbacks edit param_groups as with any optimizer
-    s_flat.fit(1, tqdm_file=None)
+    for s_ in (s_flat, s_ref):                          # schedulers / callbacks edit param_groups as with any optimizer
+        s_.optimizer.param_groups[0]["lr"] = 5e-4
+        s_.fit(2, tqdm_file=None)
+    for a, b in zip(get_params(nets_flat), get_params(nets_ref)):
+        np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-13)
 
 
 def test_training_converges_to_the_analytic_solution_cpu():
