@@ -431,6 +431,57 @@ class FusedProblem:
         self.kernel_launches += 5 if train else 3
         return self.sumsq
 
+    def train_step_graphed(self, coords, optimizer, n_global=None):
+        """One WHOLE training step as a single CUDA-graph replay: zero the gradient buffer, K0..K2b on ``coords`` and the
+        parameter update of a capturable :class:`neurodiffeq_b200.optim.FlatAdam` (its step is a fixed sequence of device
+        operations).  Returns ``self.sumsq`` (sum of squared residuals of the step, BEFORE the update).
+        Not used by the solvers yet -- added for the fit-loop work of round 2; single rank only."""
+        if not getattr(optimizer, "capturable", False):
+            raise ValueError("train_step_graphed needs FlatAdam(..., capturable=True)")
+        n = coords[0].numel()
+        n_glob = n if n_global is None else n_global
+        key = ("step", int(n), int(n_glob), id(optimizer))
+        st = self._graphs.get(key)
+        if st is None:
+            dev = self.device
+            static = [torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(self.n_coords)]
+            pinned = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(self.n_coords)]
+
+            def body():
+                self.gradbuf.zero_()
+                self.residual_grad(static, n_global=n_glob, sumsq_out=self.sumsq)
+                optimizer._step_on_device()
+
+            saved = [t.clone() for t in (self.theta, self.gradbuf, optimizer._m, optimizer._v, optimizer._t_dev)]
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                body()                       # warm-up: sizes buffers, sets kernel attributes
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+            torch.cuda.synchronize(dev)
+            for dst, src in zip((self.theta, self.gradbuf, optimizer._m, optimizer._v, optimizer._t_dev), saved):
+                dst.copy_(src)               # neither the warm-up nor the capture may count as a step
+            st = (graph, static, pinned)
+            self._graphs[key] = st
+        graph, static, pinned = st
+        optimizer.sync_hyperparameters()
+        for dst, pin, src in zip(static, pinned, coords):
+            src = src.detach().reshape(-1)
+            if src.device.type != "cpu":
+                dst.copy_(src)
+            elif src.is_pinned() and src.dtype == torch.float32 and src.is_contiguous():
+                dst.copy_(src, non_blocking=True)
+            else:
+                np.copyto(pin.numpy(), src.numpy(), casting="same_kind")
+                dst.copy_(pin, non_blocking=True)
+        graph.replay()
+        optimizer._t += 1
+        self.kernel_launches += 5
+        return self.sumsq
+
     # ---- debugging / tests: raw views of the workspace -----------------------------------------------------------------
     def flat_params_numpy(self):
         return self.theta.detach().cpu().numpy().copy()
