@@ -77,6 +77,9 @@ class CpuFusedProblem:
             sumsq_out += float((out["residual"] ** 2).sum())
         return sumsq_out, (torch.from_numpy(out["residual"]) if want_residual else None)
 
+    def grads_as_list(self):
+        return [self.grad[o:o + p.numel()].view(p.shape).detach().numpy().copy() for p, o in zip(self.params, self.offsets)]
+
     def residual_grad_graphed(self, coords, n_global=None, train=True):
         if train:
             self.residual_grad(coords, n_global=n_global, sumsq_out=self.sumsq)
