@@ -4,8 +4,8 @@
 dL/dr on the small residual matrix, the kernels do the rest).  ``h1`` adds, per coordinate, the derivative of the
 (equation-summed) residual -- ``grad(residual, *coords)`` of losses.py:18 differentiates the SUM of the residual columns
 -- and averages the squares of all ``n_eq + d`` columns: the fused solvers obtain those columns by differentiating the
-traced residuals symbolically, i.e. the same fused mean-squared path over an augmented residual list.  ``h1 semi`` (the
-derivative columns only) would leave the user's residuals outside the traced program and is not provided.
+traced residuals symbolically, i.e. the same fused mean-squared path over an augmented residual list.  ``h1 semi`` uses the
+derivative columns only; the user's residuals stay available (``get_residuals``) as auxiliary outputs of the forward kernel.
 """
 import torch
 
@@ -34,6 +34,20 @@ def _h1_semi_norm(residual, funcs, coords):
 
 
 _losses = {"l1": _l1_norm, "l2": _l2_norm, "infinity": _infinity_norm, "h1": _h1_norm, "h1 semi": _h1_semi_norm}
+
+
+def h1_semi_rows(diff_eqs, n_funcs):
+    """rows of the 'h1 semi' loss: d(sum of the equations)/d(coord) for every coordinate, without the equations"""
+    from .neurodiffeq import diff
+
+    def rows(*variables):
+        res = diff_eqs(*variables)
+        res = list(res) if isinstance(res, (list, tuple)) else [res]
+        total = res[0]
+        for r in res[1:]:
+            total = total + r
+        return [diff(total, c) for c in variables[n_funcs:]]
+    return rows
 
 
 def h1_rows(diff_eqs, n_funcs):

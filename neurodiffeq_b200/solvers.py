@@ -26,7 +26,7 @@ import torch.nn as nn
 from .conditions import BaseCondition
 from .engine import FusedProblem
 from ._compat import renamed_arguments
-from .losses import _losses, h1_rows
+from .losses import _losses, h1_rows, h1_semi_rows
 from .generators import Generator1D, Generator2D, GeneratorSpherical, SamplerGenerator
 from .networks import FCNN
 from .parallel import shard_bounds
@@ -143,10 +143,16 @@ class BaseSolver:
             n_coords = len(self.generator["train"].get_examples())
         self.n_coords = n_coords
         self._set_loss_fn(loss_fn)      # before tracing: the 'h1' loss adds derivative rows to the traced residuals
-        self.problem = FusedProblem(self.nets, self.conditions,
-                                    self._h1_rows if self._h1 else self._traced_diff_eqs, n_coords,
-                                    coords_for_condition=self._coords_for_condition, device=device)
-        self.n_eq = self.problem.n_eq - (n_coords if self._h1 else 0)     # the user's equations
+        if self._h1 == "semi":   # loss rows: derivative rows only; the user's residuals ride along as auxiliary outputs
+            self.problem = FusedProblem(self.nets, self.conditions, h1_semi_rows(self._traced_diff_eqs, self.n_funcs),
+                                        n_coords, coords_for_condition=self._coords_for_condition, device=device,
+                                        aux_outputs=self._traced_diff_eqs)
+            self.n_eq = len(self.problem.tp.aux_rows)
+        else:
+            self.problem = FusedProblem(self.nets, self.conditions,
+                                        self._h1_rows if self._h1 else self._traced_diff_eqs, n_coords,
+                                        coords_for_condition=self._coords_for_condition, device=device)
+            self.n_eq = self.problem.n_eq - (n_coords if self._h1 else 0)     # the user's equations
         self.device = self.problem.device
 
         self.optimizer = optimizer if optimizer else torch.optim.Adam(
@@ -238,8 +244,8 @@ class BaseSolver:
             self.loss_fn = _losses[name]
             if name == "h1":      # fused: mean square over [equations | d(sum of equations)/d(coords)], see _h1_rows
                 self._h1 = True
-            elif name == "h1 semi":
-                raise NotImplementedError("loss 'h1 semi' is not available in the fused solvers (see losses.py)")
+            elif name == "h1 semi":  # fused: mean square over the derivative rows only, see losses.h1_semi_rows
+                self._h1 = "semi"
             else:                 # 'l1', 'infinity': autograd on the residual matrix -> dL/dr -> kernels
                 self._custom_loss = self.loss_fn
         elif callable(criterion):
@@ -483,15 +489,18 @@ class BaseSolver:
         coords = [c if isinstance(c, torch.Tensor) else torch.as_tensor(np.asarray(c)) for c in coords]
         shape = coords[0].shape
         fp = self.problem
+        aux = fp.tp.aux_rows              # 'h1 semi': the user's residuals are auxiliary rows of u, not loss rows
+        flat = [c.reshape(-1) for c in coords]
         if best and self.best_nets_theta is not None:
             live = fp.theta.clone()
             fp.theta.copy_(self.best_nets_theta)
-            _, r, _ = fp.forward([c.reshape(-1) for c in coords], want_u=False, want_residual=True)
+            u, r, _ = fp.forward(flat, want_u=bool(aux), want_residual=not aux)
             fp.theta.copy_(live)
             fp.pack()
         else:
-            _, r, _ = fp.forward([c.reshape(-1) for c in coords], want_u=False, want_residual=True)
-        rs = [r[e].reshape(-1, 1) if no_reshape else r[e].reshape(shape) for e in range(self.n_eq)]
+            u, r, _ = fp.forward(flat, want_u=bool(aux), want_residual=not aux)
+        rows = [u[k] for k in aux] if aux else [r[e] for e in range(self.n_eq)]
+        rs = [x.reshape(-1, 1) if no_reshape else x.reshape(shape) for x in rows]
         if to_numpy:
             rs = [x.detach().cpu().numpy() for x in rs]
         return rs if len(rs) > 1 else rs[0]

@@ -75,7 +75,7 @@ class NetDescription:
 
 class TracedProblem:
     def __init__(self, nets, conditions, diff_eqs, n_coords, coords_for_condition=None, pad_scheme=None,
-                 combine_seconds=None):
+                 combine_seconds=None, aux_outputs=None):
         """``nets[k]`` / ``conditions[k]`` as in the reference solver; ``diff_eqs(*funcs, *coords)``.
         ``coords_for_condition(k, cond, coords) -> tuple`` lets SolverSpherical trim coordinates
         (reference solvers.py:894-916)."""
@@ -98,6 +98,14 @@ class TracedProblem:
                 self.func_rows.append([len(funcs)])
                 funcs.append(f)
         res = diff_eqs(*func_args, *coords) if diff_eqs is not None else []   # None: solution-only problem (u, no residual)
+        # auxiliary per-point outputs (same arguments as diff_eqs): extra rows of `u` behind the functions, evaluated by
+        # the forward kernel but not part of any loss (the 'h1 semi' loss keeps the user's residuals available this way)
+        self.aux_rows = []
+        if aux_outputs is not None:
+            aux = aux_outputs(*func_args, *coords)
+            aux = list(aux) if isinstance(aux, (list, tuple)) else [aux]
+            self.aux_rows = list(range(len(funcs), len(funcs) + len(aux)))
+            funcs += [g.lift(a) for a in aux]
         if isinstance(res, S.Sym) or not hasattr(res, "__len__"):
             res = [res]
         if any(isinstance(r, S.SymColumns) for r in res):

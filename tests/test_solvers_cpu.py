@@ -37,7 +37,7 @@ def test_fit_tracks_oracle_adam_cpu(key):
     assert solver.global_epoch == epochs and solver.lowest_loss == min(solver.metrics_history["valid_loss"])
 
 
-@pytest.mark.parametrize("loss_name", ["l1", "infinity", "h1"])
+@pytest.mark.parametrize("loss_name", ["l1", "infinity", "h1", "h1 semi"])
 def test_named_losses_cpu(loss_name):
     key, n, epochs = "c1", 120, 4
     wl, solver, nets, coords_np = make_solver(key, n, loss_fn=loss_name)
@@ -54,8 +54,6 @@ def test_named_losses_cpu(loss_name):
 def test_loss_name_errors_cpu():
     with pytest.raises(KeyError):
         make_solver("c1", 16, loss_fn="l3")
-    with pytest.raises(NotImplementedError):
-        make_solver("c1", 16, loss_fn="h1 semi")
 
 
 def test_custom_loss_callable_and_solution_cpu():
