@@ -12,7 +12,7 @@ User-supplied boundary callables (``x_min_val=lambda y: torch.sin(np.pi*y)`` ...
 
 Implemented: NoCondition :205-222, IVP :225-267, BundleIVP :270-345, DirichletBVP :398-435,
 BundleDirichletBVP :348-395, DirichletBVP2D :438-509, IBVP1D Dirichlet-Dirichlet :661-681,
-IBVP1D with Neumann data :670-701, DoubleEndedBVP1D :715-883, DirichletBVPSpherical :887-956,
+IBVP1D with Neumann data on one or both ends :670-701, DoubleEndedBVP1D :715-883, DirichletBVPSpherical :887-956,
 InfDirichletBVPSpherical :960-1019.  The Neumann flavours evaluate the network AT a boundary abscissa
 (conditions.py:585-596, 823-834): traced as a second instance of the same network fed by a constant coordinate.
 """

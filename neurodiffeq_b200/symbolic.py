@@ -763,25 +763,33 @@ class ChannelScheme:
     second derivatives D_v D_v of the FIRST n2 directions.  Mixed partials are obtained by polarisation:
     d2/dxi dxj = ( D_{ei+ej}^2 - D_ei^2 - D_ej^2 ) / 2, so pure directional seconds suffice for every order-2 jet."""
 
-    def __init__(self, n_coords, multi_indices):
+    def __init__(self, n_coords, multi_indices, merged=None):
+        """``merged``: optional list of coordinate groups that may share ONE direction because no network instance takes
+        two members of a group as inputs (constant coordinates of different boundary instances): the direction is the sum
+        of the group's axes, and restricted to any instance's inputs it is the axis of the one member that instance sees."""
+        self.n_coords = n_coords
+        self._group = {}
+        for grp in (merged or []):
+            for i in grp:
+                self._group[i] = tuple(sorted(grp))
         firsts, seconds = set(), set()
         self.mixed = set()
         for alpha in multi_indices:
             if len(alpha) == 0:
                 continue
             if len(alpha) == 1:
-                firsts.add(self._axis(n_coords, alpha[0]))
+                firsts.add(self.axis(alpha[0]))
             elif len(alpha) == 2:
                 i, j = alpha
                 if i == j:
-                    seconds.add(self._axis(n_coords, i))
+                    seconds.add(self.axis(i))
                 else:
+                    if self.axis(i) == self.axis(j):
+                        raise NotImplementedError("mixed derivative w.r.t. two coordinates that share a jet direction")
                     self.mixed.add((i, j))
-                    seconds.add(self._axis(n_coords, i))
-                    seconds.add(self._axis(n_coords, j))
-                    v = [0.0] * n_coords
-                    v[i] = v[j] = 1.0
-                    seconds.add(tuple(v))
+                    seconds.add(self.axis(i))
+                    seconds.add(self.axis(j))
+                    seconds.add(self.mixed_dir(i, j))
             else:
                 raise NotImplementedError(
                     f"derivative of order {len(alpha)} of a network output: the fused kernels carry jets up to "
@@ -793,7 +801,17 @@ class ChannelScheme:
         first_only = sorted(firsts - seconds, key=key)
         self.dirs = sec_sorted + first_only
         self.n1, self.n2 = len(self.dirs), len(sec_sorted)
-        self.n_coords = n_coords
+
+    def axis(self, i):
+        """direction vector that differentiates w.r.t. coordinate i (its whole group when directions are shared)"""
+        v = [0.0] * self.n_coords
+        for k in self._group.get(i, (i,)):
+            v[k] = 1.0
+        return tuple(v)
+
+    def mixed_dir(self, i, j):
+        """polarisation direction for d2/dxi dxj"""
+        return tuple(a + b for a, b in zip(self.axis(i), self.axis(j)))
 
     def pad_to(self, n1, n2):
         """Add inert channels (zero direction vectors / unused second-order slots) up to a compiled (n1, n2)."""
@@ -801,12 +819,6 @@ class ChannelScheme:
             raise ValueError("cannot shrink a channel scheme")
         self.dirs = list(self.dirs) + [tuple([0.0] * self.n_coords)] * (n1 - self.n1)
         self.n1, self.n2 = n1, n2
-
-    @staticmethod
-    def _axis(n_coords, i):
-        v = [0.0] * n_coords
-        v[i] = 1.0
-        return tuple(v)
 
     @property
     def n_channels(self):
@@ -816,7 +828,7 @@ class ChannelScheme:
         """channel index of a (non-mixed) multi-index."""
         if len(alpha) == 0:
             return 0
-        d = self.dirs.index(self._axis(self.n_coords, alpha[0]))
+        d = self.dirs.index(self.axis(alpha[0]))
         if len(alpha) == 1:
             return 1 + d
         assert alpha[0] == alpha[1] and d < self.n2

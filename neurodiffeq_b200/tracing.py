@@ -128,7 +128,7 @@ class TracedProblem:
             if o >= self.nets[net_idx].n_out:
                 raise ValueError(f"condition selects output unit {o} of a network with "
                                  f"{self.nets[net_idx].n_out} outputs")
-        self.scheme = S.ChannelScheme(n_coords, [n.imm[2] for n in leaves])
+        self.scheme = S.ChannelScheme(n_coords, [n.imm[2] for n in leaves], merged=self._mergeable_constant_coords())
         if pad_scheme is not None:  # round the scheme up to one the engine has a compiled kernel for
             self.scheme.pad_to(*pad_scheme(self.scheme.n1, self.scheme.n2))
         C = self.scheme.n_channels
@@ -144,9 +144,7 @@ class TracedProblem:
             net_idx, o, alpha = n.imm
             if len(alpha) == 2 and alpha[0] != alpha[1]:
                 i, j = alpha
-                v = [0.0] * n_coords
-                v[i] = v[j] = 1.0
-                cd = self.scheme.second_channel_of_dir(v)
+                cd = self.scheme.second_channel_of_dir(self.scheme.mixed_dir(i, j))
                 mapping[n] = g.mul(0.5, g.sub(g.sub(g.ych(net_idx, o, cd),
                                                     g.ych(net_idx, o, self.scheme.channel_of((i, i)))),
                                               g.ych(net_idx, o, self.scheme.channel_of((j, j)))))
@@ -180,6 +178,21 @@ class TracedProblem:
                                  + [(S.OP_ST_R, e, r) for e, r in enumerate(self.residuals)], yrow)
         self.prog_train = self._train_program(external_rbar=False)
         self._prog_train_ext = None
+
+    def _mergeable_constant_coords(self):
+        """Constant coordinates (boundary abscissae) that never feed the same network instance can share one jet
+        direction: e.g. IBVP1D with Neumann data on both ends evaluates the net at (x0, t) and at (x1, t) -- the
+        derivative directions of x0 and x1 merge, and 4 directions (x, t, boundary, t + boundary) serve both instances."""
+        consts = list(range(self.n_sampled, self.n_coords))
+        groups = []
+        for c in consts:
+            for grp in groups:
+                if all(not (c in nd.in_coord and m in nd.in_coord) for m in grp for nd in self.nets):
+                    grp.append(c)
+                    break
+            else:
+                groups.append([c])
+        return [g for g in groups if len(g) > 1]
 
     @property
     def n_channels(self):

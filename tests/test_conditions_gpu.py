@@ -64,15 +64,3 @@ def test_boundary_values_are_satisfied():
     r = r.cpu().numpy()
     assert abs(r[0, 0] - 1.0) < 1e-5      # u(x0) = 1.0
     assert abs(r[1, 1] - 0.5) < 1e-4      # u'(x1) = 0.5
-
-
-def test_unsupported_neumann_neumann_heat_is_refused():
-    """IBVP1D with Neumann data on BOTH ends of a PDE in (x, t) needs 6 jet directions (x, t, two boundary abscissae and
-    two polarisation directions); the kernels carry 4: a clear error, not a wrong answer."""
-    from neurodiffeq_b200 import diff
-    from neurodiffeq_b200.engine import FusedProblem
-    nd = product_namespace()
-    net = nd.FCNN(n_input_units=2, n_output_units=1, hidden_units=(16,))
-    cond = nd.IBVP1D(0.0, 1.0, 0.0, t_min_val=lambda x: 0 * x, x_min_prime=lambda t: 0 * t, x_max_prime=lambda t: 0 * t)
-    with pytest.raises(NotImplementedError):
-        FusedProblem([net], [cond], lambda u, x, t: [diff(u, t) - diff(u, x, order=2)], 2)

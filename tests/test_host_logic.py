@@ -124,9 +124,14 @@ def test_unsupported_features_raise_loudly():
     tp = TracedProblem([net], [IBVP1D(0, 1, 0, lambda x: x, x_min_prime=lambda t: 0, x_max_val=lambda t: 0)], heat, 2)
     assert tp.const_coords == (0.0,) and tp.n_coords == 3 and [nd.in_coord for nd in tp.nets] == [(0, 1), (2, 1)]
     assert tp.nets[0].module is tp.nets[1].module
-    with pytest.raises(NotImplementedError):   # Neumann data on both ends of a PDE: 6 jet directions, the kernels carry 4
+    # Neumann data on both ends: the two boundary abscissae never feed the same instance and share one jet direction
+    both = TracedProblem([net], [IBVP1D(0, 1, 0, lambda x: x, x_min_prime=lambda t: 0, x_max_prime=lambda t: 0)], heat, 2)
+    assert both.const_coords == (0.0, 1.0) and (both.scheme.n1, both.scheme.n2) == (4, 4)
+    assert (0.0, 0.0, 1.0, 1.0) in both.scheme.dirs and (0.0, 1.0, 1.0, 1.0) in both.scheme.dirs
+    with pytest.raises(NotImplementedError):   # all three mixed partials in 3-D: 6 jet directions, the kernels carry 4
         from neurodiffeq_b200.engine import pad_scheme
-        TracedProblem([net], [IBVP1D(0, 1, 0, lambda x: x, x_min_prime=lambda t: 0, x_max_prime=lambda t: 0)], heat, 2,
+        TracedProblem([FCNN(3, 1)], [NoCondition()],
+                      lambda u, x, y, z: [diff(diff(u, x), y) + diff(diff(u, x), z) + diff(diff(u, y), z)], 3,
                       pad_scheme=pad_scheme)
     with pytest.raises(RuntimeError):          # a boundary leaf outside a trace has no meaning
         S.Graph().const_coord(1.0)

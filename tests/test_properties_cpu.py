@@ -89,6 +89,24 @@ def test_ibvp1d_with_every_dirichlet_neumann_combination():
         close(r[0] if kind[1] == "d" else r[1], 1.0 + 0.1 * s if kind[1] == "d" else 0.1 * s)
 
 
+def test_heat_equation_residual_with_neumann_data_on_both_ends_matches_autograd():
+    """IBVP1D with two Neumann ends inside a PDE: mixed derivatives d2/dt dx0 and d2/dt dx1 of the two boundary instances
+    ride on ONE shared polarisation direction; the residual equals the oracle's autograd residual."""
+    from oracle import reference_port as oracle
+    torch.manual_seed(6)
+    net = FCNN(2, 1, hidden_units=(12, 12)).double()
+    kw = dict(x_min=0.0, x_max=1.0, t_min=0.0, t_min_val=lambda x: torch.sin(0.5 * np.pi * x),
+              x_min_prime=lambda t: 0.5 * np.pi + 0.1 * t, x_max_prime=lambda t: 0.3 * torch.sin(t))
+    heat = lambda u, x, t: [diff(u, t) - 0.3 * diff(u, x, order=2)]          # noqa: E731
+    rs = np.random.RandomState(6)
+    xs, ts = rs.rand(30), rs.rand(30)
+    _, r = evaluate([net], [C.IBVP1D(**kw)], heat, [xs, ts])
+    cols = [torch.tensor(v).reshape(-1, 1).requires_grad_(True) for v in (xs, ts)]
+    u = oracle.IBVP1D(**kw).enforce(net, *cols)
+    ref = oracle.diff(u, cols[1]) - 0.3 * oracle.diff(u, cols[0], order=2)
+    close(r[0], ref.detach().numpy()[:, 0], tol=1e-6)
+
+
 def test_box_and_spherical_dirichlet_conditions():
     torch.manual_seed(3)
     rs = np.random.RandomState(3)

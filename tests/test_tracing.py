@@ -32,7 +32,7 @@ def trace(key):
 
 EXPECTED_CHANNELS = {"c1": (1, 0), "c2": (2, 2), "c3": (2, 1), "c4": (3, 3), "c5": (1, 0),
                      # Neumann ends: the network is also evaluated at a constant coordinate; heat: x, t, boundary, t+boundary
-                     "x1": (4, 4), "x2": (4, 4), "x3": (2, 1), "x4": (2, 1), "x5": (3, 1), "x6": (1, 1),
+                     "x1": (4, 4), "x2": (4, 4), "x3": (2, 1), "x4": (2, 1), "x5": (2, 1), "x6": (1, 1), "x8": (4, 4),
                      "x7": (1, 0)}   # EnsembleCondition: one 2-output network, the function is an (N, 2) block
 
 
@@ -54,7 +54,7 @@ def test_traced_problem_matches_reference_golden(key):
 
 
 @pytest.mark.parametrize("key,wl,channels", [("c2", 2, 4), ("c4", 3, 5), ("c3", 0, 4), ("c5", 0, 2), ("x1", 4, 6),
-                                             ("x2", 4, 6), ("x5", 3, 5)])
+                                             ("x2", 4, 6), ("x8", 4, 6), ("x5", 0, 4)])
 def test_combined_second_order_channel(key, wl, channels):
     """Residuals affine in the pure second derivatives with coordinate-only coefficients are carried as ONE weighted
     channel (forward-Laplacian style): C2 5 -> 4 channels, C4 7 -> 5; values and gradients are unchanged."""

@@ -161,8 +161,10 @@ def _heat(nd, name, neumann_side):
         kw = dict(x_min=0.0, x_max=1.0, t_min=0.0, t_min_val=lambda x: torch.sin(0.5 * np.pi * x))
         if neumann_side == "right":   # Dirichlet at x0, Neumann at x1 (conditions.py:670-676)
             kw.update(x_min_val=lambda t: 0.2 * torch.sin(t), x_max_prime=lambda t: 0.1 * t)
-        else:                         # Neumann at x0, Dirichlet at x1 (conditions.py:680-686)
+        elif neumann_side == "left":  # Neumann at x0, Dirichlet at x1 (conditions.py:680-686)
             kw.update(x_min_prime=lambda t: 0.1 * t, x_max_val=lambda t: 1.0 + 0.2 * torch.sin(t))
+        else:                         # Neumann at both ends (conditions.py:689-701)
+            kw.update(x_min_prime=lambda t: 0.5 * np.pi + 0.1 * t, x_max_prime=lambda t: 0.3 * torch.sin(t))
         return [nd.IBVP1D(**kw)]
 
     def diff_eqs(u, x, t):
@@ -211,6 +213,7 @@ _EXTRA = {
     "x5": lambda nd: _bvp(nd, "x5_bvp_neumann_neumann", dict(x_min_prime=-0.5, x_max_prime=0.5)),
     "x6": lambda nd: _bvp(nd, "x6_bvp_dirichlet_dirichlet", dict(x_min_val=1.0, x_max_val=0.25)),
     "x7": _ensemble,
+    "x8": lambda nd: _heat(nd, "x8_heat_neumann_neumann", "both"),
 }
 _BUILDERS = {"c1": _c1, "c2": _c2, "c3": _c3, "c4": _c4, "c5": _c5}
 NAMES = tuple(_BUILDERS)          # BASELINE.json configs
