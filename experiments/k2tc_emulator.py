@@ -138,7 +138,7 @@ def emulate(key, n_points, T2):
     by_module, it, per_net = {}, iter(params), []
     for nd in tp.nets:
         if id(nd.module) not in by_module:
-            by_module[id(nd.module)] = [next(it) for _ in range(2 * len(nd.linears))]
+            by_module[id(nd.module)] = [next(it) for _ in range(len(nd.parameters()))]
         per_net.append(by_module[id(nd.module)])
     coords = workloads.sample_coords(wl_, n_points, seed=4)
     ref = jet_numpy.run_traced(tp, per_net, coords)

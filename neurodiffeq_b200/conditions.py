@@ -32,6 +32,17 @@ def _abs(x):
     return x.abs() if hasattr(x, "abs") else abs(x)
 
 
+def _traced_raw_output(g, net, n, o, coordinates):
+    """raw output ``o`` of registered network ``n`` as a traced expression: the jet leaf, plus -- for a Resnet -- its
+    bias-free shortcut  sum_i W_s[o][i] x_i  with the matrix entries as trainable scalars of the program"""
+    out = g.net(n, o)
+    skip = getattr(net, "skip_connection", None)
+    if skip is not None and hasattr(net, "residual"):
+        for i, c in enumerate(coordinates):
+            out = out + g.theta(("skip", id(net), o, i)) * c
+    return out
+
+
 class BaseCondition:
     """Base class (reference conditions.py:10-75): ``enforce`` = network call + ``parameterize``."""
 
@@ -50,7 +61,7 @@ class BaseCondition:
                     raise NotImplementedError("fused enforce(): the network inputs must be the sampled coordinates")
                 in_coord.append(c.imm)
             n = g.register_net(net, in_coord)
-            return g.net(n, self.ith_unit if self.ith_unit is not None else 0), n
+            return _traced_raw_output(g, net, n, self.ith_unit if self.ith_unit is not None else 0, coordinates), n
         out = net(torch.cat(coordinates, dim=1))
         if self.ith_unit is not None:
             out = out[:, self.ith_unit].view(-1, 1)
@@ -98,7 +109,8 @@ class EnsembleCondition(BaseCondition):
                 raise NotImplementedError("fused enforce(): the network inputs must be the sampled coordinates")
             in_coord.append(c.imm)
         n = g.register_net(net, in_coord)
-        return _sym.SymColumns([con.parameterize(g.net(n, i), *coordinates) for i, con in enumerate(self.conditions)])
+        return _sym.SymColumns([con.parameterize(_traced_raw_output(g, net, n, i, coordinates), *coordinates)
+                                for i, con in enumerate(self.conditions)])
 
     def parameterize(self, output_tensor, *input_tensors):
         if output_tensor.shape[1] != len(self.conditions):

@@ -128,10 +128,12 @@ class FusedProblem:
         self._adopt_parameters()
         self._build_spec()
         dev = self.device
-        self.prog_eval = torch.from_numpy(tp.prog_eval.code.copy()).to(dev)
-        self.prog_train = torch.from_numpy(tp.prog_train.code.copy()).to(dev)
-        self.prog_w = torch.from_numpy(tp.prog_w.code.copy()).to(dev) if tp.wl else None
+        self._register_program_scalars()
+        self.prog_eval = self._upload(tp.prog_eval)
+        self.prog_train = self._upload(tp.prog_train)
+        self.prog_w = self._upload(tp.prog_w) if tp.wl else None
         self._prog_train_ext = None
+        self._plan_cache = {}
         self._sizes_cache = {}
         self.pack_buf = None
         self.workspace = None
@@ -226,22 +228,74 @@ class FusedProblem:
                 net.b_off[l] = self._offset_of[id(lin.bias)]
         self.spec = sp
 
+    def _register_program_scalars(self):
+        """Trainable scalars that enter the residual programs directly (Resnet shortcut matrices): flat theta index per
+        key, and per Resnet instance the index tensors its gradient needs (made once: nothing is uploaded per step)."""
+        tp, dev = self.tp, self.device
+        self._theta_index, self._patch_sets, self._skips = {}, [], []
+        for k, nd in enumerate(tp.nets):
+            if nd.skip is None:
+                continue
+            base, n_in = self._offset_of[id(nd.skip.weight)], len(nd.in_coord)
+            for o in range(nd.n_out):
+                for i in range(n_in):
+                    self._theta_index[("skip", id(nd.module), o, i)] = base + o * n_in + i
+            rows = torch.tensor([tp.yrow0[k] + o * tp.n_channels for o in range(nd.n_out)], device=dev)
+            dirs = torch.as_tensor(tp.direction_matrix()[:, list(nd.in_coord)], dtype=torch.float32, device=dev)
+            self._skips.append((k, base, rows, dirs))
+
+    def _upload(self, program):
+        """device copy of a lowered program; remembers which immediates must follow the parameters (Program.patch)"""
+        dev_prog = torch.from_numpy(program.code.copy()).to(self.device)
+        if program.patch:
+            pcs = sorted(program.patch)
+            pos = torch.tensor([pc * 4 + 2 for pc in pcs], dtype=torch.int64, device=self.device)   # (op, dst, IMM, -)
+            idx = torch.tensor([self._theta_index[program.patch[pc]] for pc in pcs], dtype=torch.int64, device=self.device)
+            self._patch_sets.append((dev_prog, pos, idx))
+            dev_prog.view(-1)[pos] = self.theta[idx].view(torch.int32)
+        return dev_prog
+
+    def _apply_patches(self):
+        for dev_prog, pos, idx in self._patch_sets:      # float bits of the current parameter values into the immediates
+            dev_prog.view(-1)[pos] = self.theta[idx].view(torch.int32)
+
+    def _accumulate_shortcut_grads(self, all_coords, n):
+        """dL/dW_s of every Resnet instance from the seeds K1 left in the workspace: the raw output is (network jet +
+        shortcut jet), so the seeds dL/d(jet) serve both; d(value)/dW_s[o][i] = x_i, d(first-order channel f)/dW_s[o][i]
+        = dir_f[i], second-order channels do not depend on W_s."""
+        info = self._plan_cache.get(n)
+        if info is None:
+            info = self._plan_cache[n] = self.plan_info(n)
+        tp = self.tp
+        T, nt, n1 = info["T"], info["n_tiles"], tp.scheme.n1
+        raw = self.workspace[info["ws_seed"]: info["ws_seed"] + 4 * tp.n_yrows * T * nt].view(torch.float32)
+        seeds = raw.view(nt, tp.n_yrows, T).permute(1, 0, 2).reshape(tp.n_yrows, nt * T)[:, :n]      # [n_yrows, N]
+        for k, base, rows, dirs in self._skips:
+            nd = tp.nets[k]
+            x = torch.stack([all_coords[c] for c in nd.in_coord])                                       # [n_in, N]
+            g = seeds[rows] @ x.t()                                                                     # value channel
+            if n1:
+                first = torch.stack([seeds[rows + (1 + f)].sum(dim=1) for f in range(n1)], dim=1)       # [n_out, n1]
+                g = g + first @ dirs
+            self.grad[base: base + g.numel()] += g.reshape(-1)
+
     def enable_function_adjoints(self):
         """Prepare for losses that depend on the functions u as well as on the residuals (``ubar`` in
         :meth:`residual_grad`): upload that train program and make the value file large enough for it."""
         if getattr(self, "_prog_train_ext_u", None) is None:
             p = self.tp.prog_train_ext_u
-            self._prog_train_ext_u = torch.from_numpy(p.code.copy()).to(self.device)
+            self._prog_train_ext_u = self._upload(p)
             if p.n_slots > self.spec.n_slots:
                 self.spec.n_slots = p.n_slots
                 self._sizes_cache.clear()
+                self._plan_cache.clear()
                 self._graphs.clear()
         return self._prog_train_ext_u
 
     @property
     def prog_train_ext(self):
         if self._prog_train_ext is None:
-            self._prog_train_ext = torch.from_numpy(self.tp.prog_train_ext.code.copy()).to(self.device)
+            self._prog_train_ext = self._upload(self.tp.prog_train_ext)
         return self._prog_train_ext
 
     # ---- buffers ------------------------------------------------------------------------------------------------------
@@ -286,6 +340,7 @@ class FusedProblem:
                 self._const_coord_cache[n_points] = consts
             for k, c in enumerate(consts):
                 arr[self.n_coords + k] = c.data_ptr()
+            keep = keep + consts
         return arr, keep
 
     def _prog_w_args(self):
@@ -297,6 +352,8 @@ class FusedProblem:
         self._ensure_buffers(1, False)
         _check(self.lib.pj_pack(ctypes.byref(self.spec), self.theta.data_ptr(), self.pack_buf.data_ptr(),
                                 self._stream()), "pj_pack")
+        if self._patch_sets:
+            self._apply_patches()
         self.kernel_launches += 1
 
     def forward(self, coords, want_u=True, want_residual=True, want_sumsq=False, repack=True):
@@ -357,6 +414,8 @@ class FusedProblem:
                                          r.data_ptr() if want_residual else None, sumsq_out.data_ptr(),
                                          self.workspace.data_ptr(), self.workspace.numel(), self._stream()),
                "pj_forward_train")
+        if self._skips:
+            self._accumulate_shortcut_grads(keep, n)
         _check(self.lib.pj_backward(ctypes.byref(self.spec), ptrs, n, self.pack_buf.data_ptr(), self.grad.data_ptr(),
                                     self.workspace.data_ptr(), self.workspace.numel(), self._stream()), "pj_backward")
         self.kernel_launches += 4

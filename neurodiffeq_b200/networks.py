@@ -50,8 +50,9 @@ class FCNN(nn.Module):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# The remaining modules of the reference's networks.py.  They are ordinary torch modules (usable in eager code, same
-# semantics as the reference); the fused engine has no jet rule for them yet and says so when a solver is built with one.
+# The remaining modules of the reference's networks.py: ordinary torch modules with the reference's semantics.  The fused
+# engine runs Resnet (FCNN body on the kernels, shortcut inside the residual program); MonomialNN / Swish / APTx have no jet
+# rule in the kernels yet and a solver built with them says so.
 # ----------------------------------------------------------------------------------------------------------------------
 def _scalar(value, trainable):
     """a python float, or a 0-dim Parameter when the activation's scalars are to be learned"""

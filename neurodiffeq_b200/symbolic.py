@@ -92,6 +92,12 @@ class Graph:
     def rbar(self, e):
         return self._mk("rbar", (), int(e))
 
+    def theta(self, key):
+        """A trainable scalar that enters the residual program directly (not through a network jet): the entries of a
+        Resnet's bias-free shortcut matrix.  Constant w.r.t. the coordinates; lowered as an OP_CONST whose immediate the
+        engine re-writes whenever the parameters change (``Program.patch``)."""
+        return self._mk("theta", (), key)
+
     def param(self, k):
         return self._mk("param", (), int(k))
 
@@ -551,7 +557,7 @@ def derivative(node, i, memo=None):
         if key in memo:
             return memo[key]
         op = n.op
-        if op in ("const", "rbar", "param"):
+        if op in ("const", "rbar", "param", "theta"):
             r = g.const(0.0)
         elif op == "ych":
             raise ValueError("cannot differentiate a channel-resolved expression")
@@ -655,7 +661,7 @@ def reverse_gradients(roots_and_cotangents, wrt_filter=lambda n: n.op in ("net",
         if wrt_filter(n):
             out[n] = a_bar
             continue
-        if op in ("const", "coord", "rbar", "param", "net", "ych", "sign"):
+        if op in ("const", "coord", "rbar", "param", "theta", "net", "ych", "sign"):
             continue
         if op == "add":
             acc(n.args[0], a_bar)
@@ -843,10 +849,11 @@ class ChannelScheme:
 class Program:
     """Lowered bytecode: int32 array [len, 4]  (op, dst, a, b)  -- see csrc/pinnjet_program.cuh."""
 
-    def __init__(self, code, n_slots, exact_imm=None):
+    def __init__(self, code, n_slots, exact_imm=None, patch=None):
         self.code = np.asarray(code, dtype=np.int32).reshape(-1, 4)
         self.n_slots = n_slots
         self.exact_imm = exact_imm or {}  # instruction index -> float64 immediate (host-side checks only)
+        self.patch = patch or {}          # instruction index -> key of the trainable scalar its immediate must hold
 
     def __len__(self):
         return self.code.shape[0]
@@ -872,7 +879,7 @@ def lower(outputs, yrow_of):
     for op, index, s in outputs:
         store_at.setdefault(s.idx, []).append((op, index))
         last_use[s.idx] = max(last_use.get(s.idx, -1), pos[s.idx])  # store happens right after definition
-    free, slot_of, code, n_slots, exact = [], {}, [], 0, {}
+    free, slot_of, code, n_slots, exact, patch = [], {}, [], 0, {}, {}
     for k, n in enumerate(order):
         # allocate destination (operands may be released first only if this is their last use -> allows dst==src)
         srcs = [slot_of[a.idx] for a in n.args]
@@ -889,6 +896,9 @@ def lower(outputs, yrow_of):
         if op == "const":
             exact[len(code)] = n.imm
             code.append((OP_CONST, dst, _f32_bits(n.imm), 0))
+        elif op == "theta":
+            patch[len(code)] = n.imm
+            code.append((OP_CONST, dst, 0, 0))
         elif op == "coord":
             code.append((OP_COORD, dst, n.imm, 0))
         elif op == "ych":
@@ -910,7 +920,7 @@ def lower(outputs, yrow_of):
             code.append((st_op, index, dst, 0))
         if last_use.get(n.idx, -1) <= k:  # dead right away (store-only value)
             free.append(dst)
-    return Program(code, max(n_slots, 1), exact)
+    return Program(code, max(n_slots, 1), exact, patch)
 
 
 def depends_on_jets(expr):
@@ -918,8 +928,9 @@ def depends_on_jets(expr):
     return any(n.op in ("net", "ych") for n in topo_order([expr]))
 
 
-def evaluate_program(program, coords, y, rbar=None, params=None, n_u=0, n_r=0, n_seed=0, n_w=0):
-    """Pure-numpy interpreter of the bytecode (host-side check of the lowering; float64)."""
+def evaluate_program(program, coords, y, rbar=None, params=None, n_u=0, n_r=0, n_seed=0, n_w=0, theta=None):
+    """Pure-numpy interpreter of the bytecode (host-side check of the lowering; float64).  ``theta``: values of the
+    trainable scalars the program's patched constants stand for (``Program.patch`` keys -> float)."""
     n = coords.shape[1]
     val = np.zeros((program.n_slots, n))
     u, r, seed = np.zeros((n_u, n)), np.zeros((n_r, n)), np.zeros((n_seed, n))
@@ -930,7 +941,7 @@ def evaluate_program(program, coords, y, rbar=None, params=None, n_u=0, n_r=0, n
           OP_SINH: np.sinh, OP_COSH: np.cosh, OP_ATAN: np.arctan}
     for pc, (op, dst, a, b) in enumerate(program.code.tolist()):
         if op == OP_CONST:
-            val[dst] = program.exact_imm.get(pc, bits(a))
+            val[dst] = theta[program.patch[pc]] if pc in program.patch else program.exact_imm.get(pc, bits(a))
         elif op == OP_COORD:
             val[dst] = coords[a]
         elif op == OP_NET:

@@ -24,6 +24,12 @@ class NetDescription:
     def __init__(self, module, in_coord):
         self.module = module
         self.in_coord = tuple(in_coord)
+        self.skip = None
+        if hasattr(module, "residual") and hasattr(module, "skip_connection"):   # Resnet (reference networks.py:73-106)
+            self.skip = module.skip_connection
+            if not isinstance(self.skip, nn.Linear) or self.skip.bias is not None:
+                raise NotImplementedError("a Resnet shortcut must be a bias-free nn.Linear")
+            module = module.residual
         seq = getattr(module, "NN", module)
         if not isinstance(seq, nn.Sequential):
             raise NotImplementedError(
@@ -58,6 +64,8 @@ class NetDescription:
         for a, b in zip(self.linears[:-1], self.linears[1:]):
             if a.out_features != b.in_features:
                 raise ValueError("inconsistent layer widths")
+        if self.skip is not None and (self.skip.in_features, self.skip.out_features) != (self.widths[0], self.widths[-1]):
+            raise ValueError("Resnet shortcut and body disagree on the input / output widths")
         if self.widths[0] != len(self.in_coord):
             raise ValueError(f"network expects {self.widths[0]} inputs but the condition passes "
                              f"{len(self.in_coord)} coordinates")
@@ -70,6 +78,8 @@ class NetDescription:
         out = []
         for m in self.linears:
             out += [m.weight, m.bias]
+        if self.skip is not None:
+            out.append(self.skip.weight)
         return out
 
 

@@ -121,15 +121,23 @@ def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True, rbar=N
     dirs = np.asarray(tp.scheme.dirs, dtype=np.float64).reshape(tp.scheme.n1, tp.n_coords)
     n1, n2 = tp.scheme.n1, tp.scheme.n2
     C = tp.n_channels
+    theta = {}      # trainable scalars that enter the residual program directly: Resnet shortcut matrices
+    for k, nd in enumerate(tp.nets):
+        if getattr(nd, "skip", None) is not None:
+            w_skip = np.asarray(params_per_net[k][2 * len(nd.linears)], dtype=np.float64)
+            for o in range(w_skip.shape[0]):
+                for i in range(w_skip.shape[1]):
+                    theta[("skip", id(nd.module), o, i)] = w_skip[o, i]
     wl_all = None
     if getattr(tp, "wl", 0):
-        wl_all = S.evaluate_program(tp.prog_w, coords, np.zeros((1, N)), n_w=len(tp.nets) * tp.wl)
+        wl_all = S.evaluate_program(tp.prog_w, coords, np.zeros((1, N)), n_w=len(tp.nets) * tp.wl, theta=theta)
     y_rows = np.zeros((tp.n_yrows, N))
     stores = []
     for k, nd in enumerate(tp.nets):
         wl = wl_all[k * tp.wl:(k + 1) * tp.wl] if wl_all is not None else None
-        Ws = [np.asarray(p, dtype=np.float64) for p in params_per_net[k][0::2]]
-        bs = [np.asarray(p, dtype=np.float64) for p in params_per_net[k][1::2]]
+        body = params_per_net[k][:2 * len(nd.linears)]
+        Ws = [np.asarray(p, dtype=np.float64) for p in body[0::2]]
+        bs = [np.asarray(p, dtype=np.float64) for p in body[1::2]]
         x_in = coords[list(nd.in_coord)]
         d_in = dirs[:, list(nd.in_coord)]
         z_store, y = forward_jets(Ws, bs, nd.act, x_in, d_in, n2, wl)
@@ -137,21 +145,21 @@ def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True, rbar=N
         for o in range(nd.n_out):
             for c in range(C):
                 y_rows[tp.yrow0[k] + o * C + c] = y[c, o]
-    u, r, _ = S.evaluate_program(tp.prog_eval, coords, y_rows, n_u=tp.n_funcs, n_r=tp.n_eq)
+    u, r, _ = S.evaluate_program(tp.prog_eval, coords, y_rows, n_u=tp.n_funcs, n_r=tp.n_eq, theta=theta)
     out = dict(u=u, residual=r, loss=float((r ** 2).mean()) if r.size else 0.0, y=y_rows)
     if want_grad:
         n_glob = N if n_global is None else n_global
         scale = 2.0 / (n_glob * tp.n_eq)
         if rbar is None:   # L = mean(r^2) over the global batch
             _, r2, seeds = S.evaluate_program(tp.prog_train, coords, y_rows, params=[scale], n_r=tp.n_eq,
-                                              n_seed=tp.n_yrows)
+                                              n_seed=tp.n_yrows, theta=theta)
         elif ubar is None:  # externally supplied dL/dr [n_eq, N] (custom loss functions)
             _, r2, seeds = S.evaluate_program(tp.prog_train_ext, coords, y_rows, rbar=np.asarray(rbar, dtype=np.float64),
-                                              params=[scale], n_r=tp.n_eq, n_seed=tp.n_yrows)
+                                              params=[scale], n_r=tp.n_eq, n_seed=tp.n_yrows, theta=theta)
         else:               # ... and dL/du [n_funcs, N] for losses that also depend on the functions
             ext = np.concatenate([np.asarray(rbar, dtype=np.float64), np.asarray(ubar, dtype=np.float64)], axis=0)
             _, r2, seeds = S.evaluate_program(tp.prog_train_ext_u, coords, y_rows, rbar=ext, params=[scale], n_r=tp.n_eq,
-                                              n_seed=tp.n_yrows)
+                                              n_seed=tp.n_yrows, theta=theta)
         assert np.allclose(r2, r)
         by_module = {}   # instances that share a module (network evaluated at a boundary too) add up, like autograd
         for k, nd in enumerate(tp.nets):
@@ -164,6 +172,14 @@ def run_traced(tp, params_per_net, coords, n_global=None, want_grad=True, rbar=N
             mine = []
             for w, b in zip(gW, gb):
                 mine += [w, b]
+            if getattr(nd, "skip", None) is not None:
+                # shortcut matrix of a Resnet: the raw output is (network jet + shortcut jet), so both share the seeds;
+                # d(value)/dW_s[o][i] = x_i, d(first-order channel f)/dW_s[o][i] = dir_f[i], second-order channels: 0
+                g_skip = np.zeros((nd.n_out, len(nd.in_coord)))
+                for o in range(nd.n_out):
+                    for i in range(len(nd.in_coord)):
+                        g_skip[o, i] = (ybar[0, o] * x_in[i]).sum() + sum(ybar[1 + f, o].sum() * d_in[f, i] for f in range(n1))
+                mine.append(g_skip)
             acc = by_module.setdefault(id(nd.module), mine)
             if acc is not mine:
                 for a, m in zip(acc, mine):

@@ -101,6 +101,18 @@ class FCNN(nn.Module):
         return self.NN(x)
 
 
+class Resnet(nn.Module):
+    """networks.py:73-106: ``skip_connection(t) + residual(t)`` with a bias-free Linear shortcut"""
+
+    def __init__(self, n_input_units=1, n_output_units=1, actv=nn.Tanh, hidden_units=(32, 32)):
+        super().__init__()
+        self.residual = FCNN(n_input_units=n_input_units, n_output_units=n_output_units, actv=actv, hidden_units=hidden_units)
+        self.skip_connection = nn.Linear(n_input_units, n_output_units, bias=False)
+
+    def forward(self, x):
+        return self.skip_connection(x) + self.residual(x)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # conditions                                                               neurodiffeq/conditions.py
 # ----------------------------------------------------------------------------------------------------------------------
@@ -303,7 +315,7 @@ class DirichletBVPSpherical(_Condition):  # :887-956
 
 NAMESPACE = types.SimpleNamespace(
     diff=diff, grad=grad, div=div, curl=curl, laplacian=laplacian, spherical_laplacian=spherical_laplacian,
-    FCNN=FCNN, SinActv=SinActv, NoCondition=NoCondition, EnsembleCondition=EnsembleCondition, IVP=IVP, BundleIVP=BundleIVP,
+    FCNN=FCNN, Resnet=Resnet, SinActv=SinActv, NoCondition=NoCondition, EnsembleCondition=EnsembleCondition, IVP=IVP, BundleIVP=BundleIVP,
     DirichletBVP2D=DirichletBVP2D, IBVP1D=IBVP1D, DoubleEndedBVP1D=DoubleEndedBVP1D,
     DirichletBVPSpherical=DirichletBVPSpherical)
 

@@ -28,18 +28,18 @@ import ref_shim  # noqa: E402
 import workloads  # noqa: E402
 
 GOLDEN_N = {"c1": 256, "c2": 256, "c3": 256, "c4": 256, "c5": 256, "x1": 256, "x2": 256, "x3": 256, "x4": 256, "x5": 256,
-            "x6": 256, "x7": 256, "x8": 256}
+            "x6": 256, "x7": 256, "x8": 256, "x9": 256}
 
 
 def reference_namespace():
     ref_shim.import_reference()
     from neurodiffeq import diff
-    from neurodiffeq.networks import FCNN, SinActv
+    from neurodiffeq.networks import FCNN, SinActv, Resnet
     from neurodiffeq.conditions import (IVP, BundleIVP, DirichletBVP2D, IBVP1D, DirichletBVPSpherical, NoCondition,
                                         DoubleEndedBVP1D, EnsembleCondition)
     from neurodiffeq.operators import spherical_laplacian, laplacian, grad, div, curl
     return types.SimpleNamespace(
-        diff=diff, FCNN=FCNN, SinActv=SinActv, IVP=IVP, BundleIVP=BundleIVP, DirichletBVP2D=DirichletBVP2D,
+        diff=diff, FCNN=FCNN, Resnet=Resnet, SinActv=SinActv, IVP=IVP, BundleIVP=BundleIVP, DirichletBVP2D=DirichletBVP2D,
         IBVP1D=IBVP1D, DirichletBVPSpherical=DirichletBVPSpherical, NoCondition=NoCondition,
         DoubleEndedBVP1D=DoubleEndedBVP1D, EnsembleCondition=EnsembleCondition, spherical_laplacian=spherical_laplacian, laplacian=laplacian, grad=grad, div=div, curl=curl)
 

@@ -10,10 +10,10 @@ import workloads
 def product_namespace():
     from neurodiffeq_b200 import diff
     from neurodiffeq_b200 import operators as ops
-    from neurodiffeq_b200.networks import FCNN, SinActv
+    from neurodiffeq_b200.networks import FCNN, SinActv, Resnet
     from neurodiffeq_b200 import conditions as c
     return types.SimpleNamespace(
-        diff=diff, FCNN=FCNN, SinActv=SinActv, IVP=c.IVP, BundleIVP=c.BundleIVP, DirichletBVP2D=c.DirichletBVP2D,
+        diff=diff, FCNN=FCNN, Resnet=Resnet, SinActv=SinActv, IVP=c.IVP, BundleIVP=c.BundleIVP, DirichletBVP2D=c.DirichletBVP2D,
         IBVP1D=c.IBVP1D, DirichletBVPSpherical=c.DirichletBVPSpherical, NoCondition=c.NoCondition,
         DoubleEndedBVP1D=c.DoubleEndedBVP1D, EnsembleCondition=c.EnsembleCondition,
         spherical_laplacian=ops.spherical_laplacian, laplacian=ops.laplacian, grad=ops.grad, div=ops.div,

@@ -243,8 +243,8 @@ def test_deprecated_argument_names_behave_like_the_reference():
 
 
 def test_network_modules_of_the_reference():
-    """Resnet / MonomialNN / Swish / APTx (reference networks.py:73-208, tests/test_networks.py): eager semantics; a fused
-    solver refuses them with a clear NotImplementedError instead of computing something else."""
+    """Resnet / MonomialNN / Swish / APTx (reference networks.py:73-208, tests/test_networks.py): eager semantics; the fused
+    path runs Resnet (body on the kernels, shortcut in the program) and refuses the others with a clear NotImplementedError."""
     import torch.nn as nn
     from neurodiffeq_b200.networks import FCNN, Resnet, MonomialNN, Swish, APTx
     from neurodiffeq_b200.conditions import NoCondition
@@ -267,6 +267,55 @@ def test_network_modules_of_the_reference():
     assert len(list(Swish(trainable=True).parameters())) == 1 and len(list(Swish().parameters())) == 0
     assert torch.allclose(APTx(1.0, 2.0, 0.5)(x), (1.0 + torch.tanh(2.0 * x)) * 0.5 * x)
     assert len(list(APTx(trainable=True).parameters())) == 3
-    for net in (Resnet(1, 1), FCNN(1, 1, actv=Swish), nn.Sequential(MonomialNN(2), nn.Linear(2, 1))):
+    tp = TracedProblem([Resnet(1, 1)], [NoCondition()], lambda u, t: [diff(u, t)], 1)     # Resnet: body + program scalars
+    assert tp.nets[0].skip is not None and len(tp.prog_eval.patch) == 1
+    for net in (FCNN(1, 1, actv=Swish), nn.Sequential(MonomialNN(2), nn.Linear(2, 1))):
         with pytest.raises(NotImplementedError):
             TracedProblem([net], [NoCondition()], lambda u, t: [diff(u, t)], 1)
+
+
+def test_engine_helpers_for_resnet_shortcuts_on_the_cpu():
+    """The two pieces of engine logic a Resnet adds -- re-writing program immediates from the parameters and the shortcut
+    gradient from the seeds in the workspace -- are plain tensor code: exercised here on CPU tensors with a hand-laid-out
+    workspace (the layout K1 writes: [tile][row][point]) against the float64 mirror."""
+    from helpers import product_namespace, get_params
+    from neurodiffeq_b200.engine import FusedProblem, pad_scheme, combine_seconds
+    from neurodiffeq_b200.tracing import TracedProblem
+    from oracle import jet_numpy
+    wl = workloads.build(product_namespace(), "x9")
+    torch.manual_seed(5)
+    nets, conds = wl.make_nets(), wl.make_conditions()
+    tp = TracedProblem(nets, conds, wl.diff_eqs, 2, pad_scheme=pad_scheme, combine_seconds=combine_seconds)
+    fp = object.__new__(FusedProblem)                    # no CUDA library: only the pure-tensor helpers are used
+    fp.device, fp.tp = torch.device("cpu"), tp
+    fp._adopt_parameters()
+    fp._register_program_scalars()
+    n, T = 37, 16
+    coords = workloads.sample_coords(wl, n, seed=2)
+    params = get_params(nets)
+    ref = jet_numpy.run_traced(tp, [params], coords)
+    # (1) immediates follow the parameters
+    dev_prog = fp._upload(tp.prog_train)
+    pcs = sorted(tp.prog_train.patch)
+    assert pcs and all(dev_prog[pc, 0] == S.OP_CONST for pc in pcs)
+    w_skip = nets[0].skip_connection.weight.detach().float().reshape(-1)
+    got = dev_prog[pcs, 2].view(torch.float32)
+    want = torch.stack([w_skip[tp.prog_train.patch[pc][3] + 2 * tp.prog_train.patch[pc][2]] for pc in pcs])
+    assert torch.equal(got, want)
+    with torch.no_grad():
+        nets[0].skip_connection.weight.mul_(2.0)
+    fp._apply_patches()
+    assert torch.equal(dev_prog[pcs, 2].view(torch.float32), 2 * want)
+    # (2) shortcut gradient from the seeds in a workspace laid out like K1's
+    nt = (n + T - 1) // T
+    ws_seed = 256
+    seeds = np.zeros((nt, tp.n_yrows, T), dtype=np.float32)
+    for p in range(n):
+        seeds[p // T, :, p % T] = ref["seeds"][:, p]
+    fp.workspace = torch.zeros(ws_seed + seeds.nbytes, dtype=torch.uint8)
+    fp.workspace[ws_seed:] = torch.from_numpy(seeds.reshape(-1).view(np.uint8))
+    fp._plan_cache = {n: dict(T=T, n_tiles=nt, ws_seed=ws_seed)}
+    fp.grad.zero_()
+    fp._accumulate_shortcut_grads([torch.from_numpy(c) for c in coords], n)
+    base = fp._skips[0][1]
+    np.testing.assert_allclose(fp.grad[base: base + 2].numpy(), ref["grads"][-1].reshape(-1), rtol=2e-5)

@@ -23,7 +23,7 @@ def cpu_engine(monkeypatch):
     torch.set_default_dtype(old)
 
 
-@pytest.mark.parametrize("key", ["c1", "c2", "c4", "c5", "x1", "x4", "x5", "x7", "x8"])
+@pytest.mark.parametrize("key", ["c1", "c2", "c4", "c5", "x1", "x4", "x5", "x7", "x8", "x9"])
 def test_fit_tracks_oracle_adam_cpu(key):
     n, epochs = 160, 4
     wl, solver, nets, coords_np = make_solver(key, n)

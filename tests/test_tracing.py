@@ -17,7 +17,7 @@ def params_per_instance(tp, flat_params):
     by_module, it, per_net = {}, iter(flat_params), []
     for nd in tp.nets:
         if id(nd.module) not in by_module:
-            by_module[id(nd.module)] = [next(it) for _ in range(2 * len(nd.linears))]
+            by_module[id(nd.module)] = [next(it) for _ in range(len(nd.parameters()))]
         per_net.append(by_module[id(nd.module)])
     return per_net
 
@@ -32,7 +32,7 @@ def trace(key):
 
 EXPECTED_CHANNELS = {"c1": (1, 0), "c2": (2, 2), "c3": (2, 1), "c4": (3, 3), "c5": (1, 0),
                      # Neumann ends: the network is also evaluated at a constant coordinate; heat: x, t, boundary, t+boundary
-                     "x1": (4, 4), "x2": (4, 4), "x3": (2, 1), "x4": (2, 1), "x5": (2, 1), "x6": (1, 1), "x8": (4, 4),
+                     "x1": (4, 4), "x2": (4, 4), "x3": (2, 1), "x4": (2, 1), "x5": (2, 1), "x6": (1, 1), "x8": (4, 4), "x9": (2, 1),
                      "x7": (1, 0)}   # EnsembleCondition: one 2-output network, the function is an (N, 2) block
 
 

@@ -205,6 +205,22 @@ def _ensemble(nd):
                     make_conditions, diff_eqs, 2, 4096, _fcnn_flops((1, 32, 32, 2), 2), None)
 
 
+def _resnet(nd):
+    """Resnet (FCNN + bias-free shortcut, reference networks.py:73-106) on Burgers-like dynamics in (x, t)."""
+    def make_nets():
+        return [nd.Resnet(n_input_units=2, n_output_units=1, hidden_units=(32, 32))]
+
+    def make_conditions():
+        return [nd.IBVP1D(x_min=-1, x_max=1, t_min=0, t_min_val=lambda x: -torch.sin(np.pi * x),
+                          x_min_val=lambda t: 0, x_max_val=lambda t: 0)]
+
+    def diff_eqs(u, x, t):
+        return [nd.diff(u, t) + u * nd.diff(u, x) - 0.05 * nd.diff(u, x, order=2)]
+
+    return Workload("x9_resnet_burgers", "Solver2D", ("x", "t"), ((-1.0, 1.0), (0.0, 1.0)), [((2, 32, 32, 1), "tanh")],
+                    make_nets, make_conditions, diff_eqs, 1, 4096, _fcnn_flops((2, 32, 32, 1), 4), None)
+
+
 _EXTRA = {
     "x1": lambda nd: _heat(nd, "x1_heat_dirichlet_neumann", "right"),
     "x2": lambda nd: _heat(nd, "x2_heat_neumann_dirichlet", "left"),
@@ -214,6 +230,7 @@ _EXTRA = {
     "x6": lambda nd: _bvp(nd, "x6_bvp_dirichlet_dirichlet", dict(x_min_val=1.0, x_max_val=0.25)),
     "x7": _ensemble,
     "x8": lambda nd: _heat(nd, "x8_heat_neumann_neumann", "both"),
+    "x9": _resnet,
 }
 _BUILDERS = {"c1": _c1, "c2": _c2, "c3": _c3, "c4": _c4, "c5": _c5}
 NAMES = tuple(_BUILDERS)          # BASELINE.json configs
