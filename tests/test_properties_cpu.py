@@ -169,3 +169,32 @@ def test_vector_calculus_identities():
 
     _, r = evaluate([FCNN(3, 1, hidden_units=(8,))], [C.NoCondition()], radial, [xyz[0] + 0.5, xyz[1] + 0.3, xyz[2]])
     assert np.abs(r).max() < 1e-6
+
+
+def test_resnet_with_a_neumann_boundary_instance_matches_autograd():
+    """A Resnet evaluated at the sample points AND at a boundary abscissa: two instances share the body's weights and the
+    shortcut matrix; loss and every parameter gradient equal autograd's (oracle)."""
+    from oracle import reference_port as oracle
+    from neurodiffeq_b200.networks import Resnet
+    torch.manual_seed(8)
+    net = Resnet(2, 1, hidden_units=(10, 10)).double()
+    kw = dict(x_min=0.0, x_max=1.0, t_min=0.0, t_min_val=lambda x: torch.sin(0.5 * np.pi * x),
+              x_min_val=lambda t: 0.2 * torch.sin(t), x_max_prime=lambda t: 0.1 * t)
+    heat = lambda u, x, t: [diff(u, t) - 0.3 * diff(u, x, order=2)]          # noqa: E731
+    rs = np.random.RandomState(8)
+    xs, ts = rs.rand(40), rs.rand(40)
+    fp = CpuFusedProblem([net], [C.IBVP1D(**kw)], heat, 2)
+    assert len(fp.tp.nets) == 2 and fp.tp.nets[0].module is fp.tp.nets[1].module and fp.tp.nets[0].skip is not None
+    fp.gradbuf.zero_()
+    sumsq, _ = fp.residual_grad([torch.tensor(xs), torch.tensor(ts)])
+    loss = float(sumsq) / 40
+    got = {name: p.grad.clone() for name, p in net.named_parameters()}
+    for p in net.parameters():
+        p.grad = None
+    cols = [torch.tensor(v).reshape(-1, 1).requires_grad_(True) for v in (xs, ts)]
+    u = oracle.IBVP1D(**kw).enforce(net, *cols)
+    ref = ((oracle.diff(u, cols[1]) - 0.3 * oracle.diff(u, cols[0], order=2)) ** 2).mean()
+    ref.backward()
+    assert abs(loss - float(ref.detach())) <= 1e-6 * float(ref.detach())
+    for name, p in net.named_parameters():
+        np.testing.assert_allclose(got[name].numpy(), p.grad.numpy(), rtol=2e-6, atol=1e-9, err_msg=name)
