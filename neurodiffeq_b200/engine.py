@@ -107,7 +107,8 @@ def pad_scheme(n1, n2):
 class FusedProblem:
     """Device state for one (nets, conditions, diff_eqs): spec, programs, flat parameter/gradient storage, workspace."""
 
-    def __init__(self, nets, conditions, diff_eqs, n_coords, coords_for_condition=None, device=None, aux_outputs=None):
+    def __init__(self, nets, conditions, diff_eqs, n_coords, coords_for_condition=None, device=None, aux_outputs=None,
+                 enforce=None):
         self.lib = load_library()
         if device is None:
             if not torch.cuda.is_available():
@@ -115,7 +116,7 @@ class FusedProblem:
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
         self.tp = TracedProblem(nets, conditions, diff_eqs, n_coords, coords_for_condition, pad_scheme=pad_scheme,
-                                combine_seconds=combine_seconds, aux_outputs=aux_outputs)
+                                combine_seconds=combine_seconds, aux_outputs=aux_outputs, enforce=enforce)
         tp = self.tp
         if (tp.scheme.n1, tp.scheme.n2) in COMBINED_ONLY and not tp.wl:
             raise NotImplementedError(

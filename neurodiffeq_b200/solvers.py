@@ -66,7 +66,7 @@ def _unique(params):
 class BaseSolution:
     """Callable solution ``u(*coords)`` evaluated by the forward kernel (reference solvers.py:650-720)."""
 
-    def __init__(self, nets, conditions, n_coords, coords_for_condition=None):
+    def __init__(self, nets, conditions, n_coords, coords_for_condition=None, enforce=None):
         if nets is None:
             raise RuntimeError("The nets cannot be None, check if you disabled validation "
                                "and used `best`=True with `get_solution` / `get_residual`")
@@ -74,11 +74,12 @@ class BaseSolution:
         self.conditions = conditions
         self._n_coords = n_coords
         self._cfc = coords_for_condition
+        self._enforce = enforce
         self._problem = None
 
     def _fused(self):
         if self._problem is None:
-            self._problem = FusedProblem(self.nets, self.conditions, None, self._n_coords, self._cfc)
+            self._problem = FusedProblem(self.nets, self.conditions, None, self._n_coords, self._cfc, enforce=self._enforce)
         return self._problem
 
     @renamed_arguments(as_type="to_numpy")                          # reference solvers.py:681
@@ -146,12 +147,13 @@ class BaseSolver:
         if self._h1 == "semi":   # loss rows: derivative rows only; the user's residuals ride along as auxiliary outputs
             self.problem = FusedProblem(self.nets, self.conditions, h1_semi_rows(self._traced_diff_eqs, self.n_funcs),
                                         n_coords, coords_for_condition=self._coords_for_condition, device=device,
-                                        aux_outputs=self._traced_diff_eqs)
+                                        aux_outputs=self._traced_diff_eqs, enforce=self.compute_func_val)
             self.n_eq = len(self.problem.tp.aux_rows)
         else:
             self.problem = FusedProblem(self.nets, self.conditions,
                                         self._h1_rows if self._h1 else self._traced_diff_eqs, n_coords,
-                                        coords_for_condition=self._coords_for_condition, device=device)
+                                        coords_for_condition=self._coords_for_condition, device=device,
+                                        enforce=self.compute_func_val)
             self.n_eq = self.problem.n_eq - (n_coords if self._h1 else 0)     # the user's equations
         self.device = self.problem.device
 
@@ -483,7 +485,8 @@ class BaseSolver:
             conditions = deepcopy(conditions)
         elif best:
             warnings.warn("copy=False with best=True returns a copy of the best networks", RuntimeWarning)
-        return self._solution_class()(nets, conditions, self.n_coords, self._coords_for_condition)
+        return self._solution_class()(nets, conditions, self.n_coords, self._coords_for_condition,
+                                      enforce=self.compute_func_val)
 
     def get_residuals(self, *coords, to_numpy=False, best=True, no_reshape=False):
         coords = [c if isinstance(c, torch.Tensor) else torch.as_tensor(np.asarray(c)) for c in coords]
@@ -621,8 +624,6 @@ class SolverSpherical(BaseSolver):
                  n_batches_valid=4, metrics=None, enforcer=None, n_output_units=1, shuffle=None, batch_size=None,
                  **kw):
         _need_bounds(r_min, r_max, ("r_min", "r_max"), train_generator, valid_generator)
-        if enforcer is not None:
-            raise NotImplementedError("custom `enforcer` callables are not supported by the fused SolverSpherical")
         if train_generator is None:
             train_generator = GeneratorSpherical(512, r_min, r_max, method="equally-spaced-noisy")
         if valid_generator is None:
@@ -635,11 +636,20 @@ class SolverSpherical(BaseSolver):
                          batch_size=batch_size, **kw)
 
     def _coords_for_condition(self, k, cond, coords):
+        if self.enforcer:                       # a user enforcer receives all three coordinates (reference :907-908)
+            return tuple(coords)
         if cond.__class__.enforce == BaseCondition.enforce:
             n_params = len(signature(cond.parameterize).parameters)
         else:
             n_params = len(signature(cond.enforce).parameters)
         return tuple(coords[:n_params - 1])
+
+    def compute_func_val(self, net, cond, *coordinates):
+        """``_auto_enforce`` of the reference (:894-916): a user ``enforcer(net, cond, coordinates)`` if given, else the
+        condition's own enforce on as many leading coordinates as it takes (trimmed by ``_coords_for_condition``)."""
+        if self.enforcer:
+            return self.enforcer(net, cond, coordinates)
+        return cond.enforce(net, *coordinates)
 
     def _solution_class(self):
         return SolutionSpherical

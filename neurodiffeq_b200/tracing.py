@@ -85,7 +85,7 @@ class NetDescription:
 
 class TracedProblem:
     def __init__(self, nets, conditions, diff_eqs, n_coords, coords_for_condition=None, pad_scheme=None,
-                 combine_seconds=None, aux_outputs=None):
+                 combine_seconds=None, aux_outputs=None, enforce=None):
         """``nets[k]`` / ``conditions[k]`` as in the reference solver; ``diff_eqs(*funcs, *coords)``.
         ``coords_for_condition(k, cond, coords) -> tuple`` lets SolverSpherical trim coordinates
         (reference solvers.py:894-916)."""
@@ -97,7 +97,9 @@ class TracedProblem:
         func_args, funcs, self.func_rows = [], [], []     # func_rows[k]: rows of u that make up function k (1 unless ensemble)
         for k, (net, cond) in enumerate(zip(nets, conditions)):
             cc = coords if coords_for_condition is None else coords_for_condition(k, cond, coords)
-            f = cond.enforce(net, *cc)
+            # `enforce(net, cond, *coords)`: the solver's `compute_func_val` hook (reference solvers.py:267-279), which users
+            # may override; default: the condition's own enforce
+            f = cond.enforce(net, *cc) if enforce is None else enforce(net, cond, *cc)
             if isinstance(f, S.SymColumns):          # EnsembleCondition: one function = an (N, k) block of columns
                 func_args.append(f)
                 self.func_rows.append(list(range(len(funcs), len(funcs) + len(f.cols))))

@@ -11,10 +11,11 @@ from oracle import jet_numpy
 
 
 class CpuFusedProblem:
-    def __init__(self, nets, conditions, diff_eqs, n_coords, coords_for_condition=None, device=None, aux_outputs=None):
+    def __init__(self, nets, conditions, diff_eqs, n_coords, coords_for_condition=None, device=None, aux_outputs=None,
+                 enforce=None):
         self.device = torch.device("cpu")
         self.tp = TracedProblem(nets, conditions, diff_eqs, n_coords, coords_for_condition, pad_scheme=pad_scheme,
-                                combine_seconds=combine_seconds, aux_outputs=aux_outputs)
+                                combine_seconds=combine_seconds, aux_outputs=aux_outputs, enforce=enforce)
         self.n_coords, self.n_funcs, self.n_eq = n_coords, self.tp.n_funcs, self.tp.n_eq
         params, seen = [], set()
         for nd in self.tp.nets:

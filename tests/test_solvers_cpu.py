@@ -291,3 +291,37 @@ def test_bundle_and_spherical_solutions_cpu():
     assert res.shape == (5,) and np.isfinite(res).all()
     internals = solver.get_internals(["nets", "conditions"], return_type="dict")
     assert set(internals) == {"nets", "conditions"}
+
+
+def test_compute_func_val_hook_and_spherical_enforcer_cpu():
+    """Solver hooks of the reference API (solvers.py:267-279, 894-916): an overridden ``compute_func_val`` and a spherical
+    ``enforcer`` decide how a condition is applied; the fused solvers trace through them."""
+    import neurodiffeq_b200.solvers as Sv
+    from neurodiffeq_b200 import diff
+    from neurodiffeq_b200.conditions import IVP, NoCondition
+    from neurodiffeq_b200.generators import Generator1D, GeneratorSpherical
+    from neurodiffeq_b200.networks import FCNN
+
+    class Shifted(Sv.Solver1D):
+        def compute_func_val(self, net, cond, *coordinates):
+            return cond.enforce(net, *coordinates) + 2.0            # u = parameterised value + 2
+
+    g = Generator1D(16, 0.0, 1.0, "equally-spaced")
+    s = Shifted(lambda u, t: [diff(u, t)], [IVP(0.0, 1.0)], nets=[FCNN(1, 1, hidden_units=(8,))], train_generator=g,
+                valid_generator=g)
+    assert abs(float(s.get_solution(best=False)(torch.zeros(1))) - 3.0) < 1e-12
+
+    seen = []
+
+    def enforcer(net, cond, coordinates):
+        seen.append(len(coordinates))
+        r, th, ph = coordinates
+        return cond.enforce(net, r, th, ph) * (r - 1.0)             # vanishes on the unit sphere
+
+    gs = GeneratorSpherical(24, 0.5, 1.5)
+    sp = Sv.SolverSpherical(lambda u, r, th, ph: [diff(u, r)], [NoCondition()], nets=[FCNN(3, 1, hidden_units=(8,))],
+                            train_generator=gs, valid_generator=gs, enforcer=enforcer)
+    assert seen and seen[0] == 3
+    sp.fit(1, tqdm_file=None)
+    u = sp.get_solution(best=False)(np.ones(4), np.linspace(0.3, 2.0, 4), np.linspace(0.1, 3.0, 4), to_numpy=True)
+    assert np.allclose(u, 0.0, atol=1e-12)
