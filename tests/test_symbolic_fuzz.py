@@ -78,3 +78,53 @@ def test_traced_expression_and_derivatives_match_autograd(seed):
     for k in range(2):
         ref = adj_t[k].detach().numpy()[:, 0]
         assert np.max(np.abs(seed_rows[k] - ref) / (1.0 + np.abs(ref))) < 5e-6
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_pde_residuals_value_loss_and_gradient_match_autograd(seed):
+    """End to end through the tracer, the channel scheme (incl. mixed partials by polarisation and the combined
+    second-order channel when the residual happens to be affine in u_xx, u_yy), the lowered programs and the numpy mirror
+    of the kernels -- against plain autograd on the same small network, for random residual expressions over
+    {u, u_x, u_y, u_xx, u_yy, u_xy, x, y}."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from cpu_engine import CpuFusedProblem
+    from neurodiffeq_b200.conditions import NoCondition
+    from neurodiffeq_b200.networks import FCNN
+    rs = np.random.RandomState(100 + seed)
+    torch.manual_seed(seed)
+    net = FCNN(2, 1, hidden_units=(7, 6)).double()
+    use_mixed = rs.rand() < 0.5
+    shape = random_expression(rs, [None] * 8, depth=3)
+    affine = rs.rand() < 0.4          # sometimes an affine-in-second-derivatives residual: exercises the combined channel
+
+    def residual(u, x, y):
+        ux, uy = diff(u, x), diff(u, y)
+        uxx, uyy = diff(u, x, order=2), diff(u, y, order=2)
+        if affine:
+            return [(1.0 + x * x) * uxx + torch.exp(-y) * uyy + shape([u, ux, uy, x, y, x, y, u])]
+        uxy = diff(ux, y) if use_mixed else ux * uy
+        return [shape([u, ux, uy, uxx, uyy, uxy, x, y])]
+
+    n = 23
+    xs, ys = rs.uniform(-1, 1, n), rs.uniform(-1, 1, n)
+    fp = CpuFusedProblem([net], [NoCondition()], residual, 2)
+    if affine:
+        assert fp.tp.wl == 2                      # the tracer proved affinity: one weighted second-order channel
+    fp.gradbuf.zero_()
+    sumsq, r = fp.residual_grad([torch.tensor(xs), torch.tensor(ys)], want_residual=True)
+    got_grads = [p.grad.clone() for p in net.parameters()]
+    for p in net.parameters():
+        p.grad = None
+    cx = [torch.tensor(v).reshape(-1, 1).requires_grad_(True) for v in (xs, ys)]
+    u = net(torch.cat(cx, dim=1))
+    res = residual(u, *cx)[0] + 0.0 * u
+    loss = (res ** 2).mean()
+    loss.backward()
+    scale = 1.0 + np.abs(res.detach().numpy()[:, 0])
+    assert np.max(np.abs(r.numpy()[0] - res.detach().numpy()[:, 0]) / scale) < 1e-5
+    assert abs(float(sumsq) / n - float(loss.detach())) <= 1e-5 * (1.0 + float(loss.detach()))
+    gn = np.sqrt(sum(float((p.grad ** 2).sum()) for p in net.parameters()))
+    dn = np.sqrt(sum(float(((a - p.grad) ** 2).sum()) for a, p in zip(got_grads, net.parameters())))
+    assert dn <= 1e-5 * (1.0 + gn)
