@@ -1,6 +1,6 @@
 """GPU-side stage-by-stage comparison of the kernels' buffers with the numpy mirror (oracle/jet_numpy.py).
 
-Usage (on the GPU box):  python tools/gpu_debug.py c2 [N]
+Usage (on the GPU box):  python tests/dev/gpu_debug.py c2 [N]
 Prints, per stage, the max abs error: u, residual, z-jets of every hidden layer (from the workspace), seeds,
 gradient of every parameter tensor.  Diagnostic tool; not part of the product.
 """
@@ -10,7 +10,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -6,7 +6,7 @@ as given and the KERNEL'S OWN index algebra and control flow are replayed litera
 weight addressing in the workspace layout K1 writes, the owner layout, the split-image stores, the TMEM -> staging -> owner
 transposition, the accumulator slots, the shared-memory gradient indices and the final read-out -- and the resulting
 parameter gradient is compared with the float64 mirror of the algorithm (oracle/jet_numpy.py, itself pinned against the
-reference).  Run:  python experiments/k2tc_emulator.py [c2 c5 x3:64 ...]   ("x3:64" = workload x3 with 64-wide hidden layers)
+reference).  Run:  python tests/dev/k2tc_emulator.py [c2 c5 x3:64 ...]   ("x3:64" = workload x3 with 64-wide hidden layers)
 """
 import os
 import sys
@@ -14,7 +14,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
