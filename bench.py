@@ -14,6 +14,11 @@ call with pinned HOST coordinates copied in and the loss copied out inside the t
 
 `--impl reference` times the CPU oracle port of the reference's closure (oracle/reference_port.py, torch autograd,
 float64 = the reference's default dtype) on this box's host cores for the same workload.
+
+Besides the contract's keys the line carries, at N = 1: `cpu_baseline` (the same oracle closure on a bounded sample),
+`gpu_autograd_baseline` (the reference algorithm through stock PyTorch CUDA autograd on this GPU -- what a user of the
+reference gets on a B200 today) and `fit` (the product's Solver.fit end to end: host sampling, H2D, K0..K2b, Adam,
+one loss read per epoch).  All three run AFTER the timed region.
 """
 import argparse
 import json
