@@ -27,12 +27,15 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_struct_layout_matches_c(tmp_path):
     from neurodiffeq_b200 import engine
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "pinnjet.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(PjNet), '
-                   'sizeof(PjSpec), sizeof(PjSizes));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pinnjet.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(PjNet), sizeof(PjSpec), sizeof(PjSizes), offsetof(PjSpec, dir), offsetof(PjSpec, n_theta), '
+                   'offsetof(PjSpec, net), offsetof(PjNet, w_off), offsetof(PjNet, yrow0));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
-    a, b, c = map(int, subprocess.check_output([str(exe)]).split())
+    a, b, c, o_dir, o_theta, o_net, o_woff, o_yrow = map(int, subprocess.check_output([str(exe)]).split())
     assert (a, b, c) == (ctypes.sizeof(engine.PjNet), ctypes.sizeof(engine.PjSpec), ctypes.sizeof(engine.PjSizes))
+    assert (o_dir, o_theta, o_net) == (engine.PjSpec.dir.offset, engine.PjSpec.n_theta.offset, engine.PjSpec.net.offset)
+    assert (o_woff, o_yrow) == (engine.PjNet.w_off.offset, engine.PjNet.yrow0.offset)
 
 
 def test_no_gpu_means_loud_failure():
