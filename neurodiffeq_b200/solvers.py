@@ -117,8 +117,6 @@ class BaseSolver:
         if batch_size is not None:
             warnings.warn("param `batch_size` is deprecated and ignored; specify n_batches_train and n_batches_valid",
                           FutureWarning)
-        if analytic_solutions:
-            raise NotImplementedError("`analytic_solutions` is deprecated in the reference; pass a `metrics` dict")
         self.diff_eqs = diff_eqs
         self.conditions = conditions
         self.n_funcs = len(conditions)
@@ -131,6 +129,19 @@ class BaseSolver:
         if valid_generator is None:
             raise ValueError("valid_generator must be specified")
         self.metrics_fn = metrics if metrics else {}
+        if analytic_solutions:   # legacy argument (reference solvers.py:151-172): becomes the metric 'analytic_mse'
+            warnings.warn("The `analytic_solutions` argument is deprecated and could lead to unstable behavior. "
+                          "Pass a `metrics` dict instead.", FutureWarning)
+            if "analytic_mse" in self.metrics_fn:
+                warnings.warn("Ignoring `analytic_solutions` in presence of key 'analytic_mse' in `metrics`", FutureWarning)
+            else:
+                n_in = n_input_units if self.N_COORDS is None else self.N_COORDS
+
+                def analytic_mse(*args):
+                    us, xs = args[:-n_in], args[-n_in:]
+                    return ((torch.stack(us) - torch.stack(tuple(analytic_solutions(*xs)))) ** 2).mean()
+
+                self.metrics_fn = dict(self.metrics_fn, analytic_mse=analytic_mse)
         self.metrics_history = {"train_loss": [], "valid_loss": []}
         self.metrics_history.update({"train__" + name: [] for name in self.metrics_fn})
         self.metrics_history.update({"valid__" + name: [] for name in self.metrics_fn})

@@ -165,3 +165,15 @@ class TestEvaluation:
     def test_solution_meets_the_initial_value_exactly(self):
         u = build().get_solution(best=False)
         assert (u(torch.zeros((1, 1))) == 1).all()
+
+
+def test_legacy_analytic_solutions_become_a_metric():
+    """reference solvers.py:151-172: `analytic_solutions` is deprecated but still works, as the metric 'analytic_mse'."""
+    with pytest.warns(FutureWarning):
+        s = build(analytic_solutions=lambda t: [torch.exp(-t)])
+    quiet_fit(s, epochs=2)
+    hist = s.metrics_history["train__analytic_mse"]
+    assert len(hist) == 2 and all(np.isfinite(hist)) and len(s.metrics_history["valid__analytic_mse"]) == 2
+    with pytest.warns(FutureWarning):
+        s2 = build(analytic_solutions=lambda t: [torch.exp(-t)], metrics={"analytic_mse": lambda u, t: (u * 0).mean()})
+    assert quiet_fit(s2).metrics_history["train__analytic_mse"] == [0.0]
