@@ -4,6 +4,7 @@
 # modes
 #   tests            pytest -m gpu (all) + smoke
 #   tests-tc N       the parity suite with the tensor-core forward kernel variant N (PINNJET_TC=N)
+#   tests-new        the GPU tests of features that were only CPU-verified so far (PINNJET_TEST_UNVALIDATED=1)
 #   bench [wl ...]   bench.py for the given workloads (default: c2 c3 c4 c5 c1), one JSON per workload + a summary line
 #   launches         ncu launch list of bench.py (gpu__time_duration per kernel; cold, serialised: shares only)
 #   ncu KERNEL [TC]  one `ncu --set full` capture of a kernel matching regex KERNEL (k1_forward, k2_backward, k1tc2_forward)
@@ -38,6 +39,9 @@ case "$mode" in
   tests-tc)
     PINNJET_TC=${1:-2} timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_solvers_gpu.py tests/test_properties_gpu.py \
         -m gpu -q > gpurun_out/pytest_gpu_tc.log 2>&1; tail -5 gpurun_out/pytest_gpu_tc.log ;;
+  tests-new)
+    PINNJET_TEST_UNVALIDATED=1 timeout 600 python -m pytest tests/test_conditions_gpu.py -m gpu -q > gpurun_out/pytest_gpu_new.log 2>&1
+    tail -12 gpurun_out/pytest_gpu_new.log ;;
   bench)
     wls=${@:-c2 c3 c4 c5 c1}; files=""
     for w in $wls; do
