@@ -89,14 +89,15 @@ class EnsembleCondition(BaseCondition):
 
     def __init__(self, *sub_conditions, force=False):
         super().__init__()
-        for i, c in enumerate(sub_conditions):
-            if c.__class__.enforce != BaseCondition.enforce:
-                msg = f"{c.__class__.__name__} (index={i})'s overrides BaseCondition's `.enforce` method. " \
-                      f"Ensembl'ing is likely not going to work."
-                if force:
-                    warnings.warn(msg)
-                else:
-                    raise ValueError(msg + "\nTry with `force=True` if you know what you are doing.")
+        # A sub-condition only ever sees ONE column of the shared network's output, through `parameterize`; one that
+        # replaces `enforce` itself (e.g. to evaluate the network elsewhere) cannot be composed this way.
+        custom = [(k, type(c).__name__) for k, c in enumerate(sub_conditions) if type(c).enforce is not BaseCondition.enforce]
+        if custom:
+            text = "; ".join(f"sub-condition {k} ({name}) defines its own `enforce`" for k, name in custom) + \
+                   ": an ensemble calls `parameterize` on single output columns and would bypass it"
+            if not force:
+                raise ValueError(text + " (pass force=True to build the ensemble anyway)")
+            warnings.warn(text)
         self.conditions = sub_conditions
 
     def enforce(self, net, *coordinates):
@@ -113,30 +114,29 @@ class EnsembleCondition(BaseCondition):
                                 for i, con in enumerate(self.conditions)])
 
     def parameterize(self, output_tensor, *input_tensors):
-        if output_tensor.shape[1] != len(self.conditions):
-            raise ValueError(f"number of output units ({output_tensor.shape[1]}) "
-                             f"differs from number of conditions ({len(self.conditions)})")
-        return torch.cat([con.parameterize(output_tensor[:, i].view(-1, 1), *input_tensors)
-                          for i, con in enumerate(self.conditions)], dim=1)
+        k = len(self.conditions)
+        if output_tensor.shape[1] != k:
+            raise ValueError(f"an ensemble of {k} conditions needs a network with {k} output units, got "
+                             f"{output_tensor.shape[1]}")
+        columns = output_tensor.split(1, dim=1)                       # k tensors of shape (N, 1)
+        return torch.cat([c.parameterize(col, *input_tensors) for c, col in zip(self.conditions, columns)], dim=1)
 
 
 class _BundleConditionMixin:
     """Bundle parameters are taken per point from ``thetas`` by index (reference conditions.py:78-135)."""
 
     def __init__(self, bundle_param_lookup=None, allowed_params=None):
-        self.bundle_param_lookup = bundle_param_lookup or {}
-        if isinstance(allowed_params, str):
-            allowed_params = set(allowed_params)
-        if allowed_params:
-            illegal = set(self.bundle_param_lookup) - set(allowed_params)
-            if illegal:
-                raise ValueError(f"The following parameter(s) are not allowed in `bundle_parameters_lookup`: "
-                                 f"{illegal}.\nSupported parameter name(s) are: {allowed_params}.")
+        self.bundle_param_lookup = dict(bundle_param_lookup) if bundle_param_lookup else {}
+        known = set(allowed_params) if allowed_params else None      # a str is read as a set of 1-letter names, as upstream
+        unknown = sorted(set(self.bundle_param_lookup) - known) if known else []
+        if unknown:
+            raise ValueError(f"`bundle_param_lookup` names {unknown}, which this condition does not have; "
+                             f"it accepts {sorted(known)}")
 
     def _get_parameter(self, param_name, thetas, override_name=None):
-        if param_name in self.bundle_param_lookup:
-            return thetas[self.bundle_param_lookup[param_name]]
-        return getattr(self, override_name or param_name)
+        """Per-point column of ``thetas`` when the parameter is bundled, else the fixed attribute of the condition."""
+        idx = self.bundle_param_lookup.get(param_name)
+        return getattr(self, override_name or param_name) if idx is None else thetas[idx]
 
 
 def _ivp_form(out, t, t_0, u_0, u_0_prime):

@@ -230,14 +230,32 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
         pl.resident_fwd = 1;
         if (o > SMEM_LIMIT) return fail(-2, "tensor-core forward kernel does not fit in shared memory (%d B)", o);
     } else {   // K1: act | ring | small | ycache | slots | misc | prog
-        const int act_bytes = hmax * pl.RS1 * 4;
-        const int ycache_bytes = 2 * sp.n_yrows * pl.epi_batch * 4, slots_bytes = sp.n_slots * 32 * 4;
+        // The forward CTA shape is K1's own business: it depends on the program length (which only pj_forward* know),
+        // so nothing the other entry points share (K2 tile, record layout, workspace, packed weights) may depend on it.
+        // 128-thread CTAs need every weight chunk resident; when that does not fit, K1 alone falls back to one 256-thread
+        // CTA per SM with a streamed ring -- its tile stays a multiple of the record tile T.
         const int nw = sp.n_nets * sp.wl;
-        const int wbuf_bytes = nw * pl.T1 * 4, wslots_bytes = sp.wl > 0 ? sp.n_slots * pl.ntc1 * 4 : 0;
-        const int fixed = act_bytes + small_bytes + ycache_bytes + slots_bytes + misc_bytes + wbuf_bytes + wslots_bytes +
-                          (prog_len + prog_w_len) * 16;
-        // 128-thread forward CTAs share one service warp between weight loading and the residual program -> resident only
-        const int ns = pick_stages(fixed, pl.chunks_fwd, pl.ntc1 == 128 ? 3 : 1, pl.ntc1 == 128);
+        int ns = -1, act_bytes = 0, ycache_bytes = 0, slots_bytes = 0, wbuf_bytes = 0, wslots_bytes = 0;
+        for (int attempt = 0; attempt < 2 && ns < 0; ++attempt) {
+            if (attempt == 1) {
+                if (pl.ntc1 == 256) break;
+                pl.ntc1 = 256;
+                pl.T1 = pl.ntc1 * pl.P1 * pl.Q1 / hmax;
+                if ((pl.T1 / pl.P1) % 8 != 0 || pl.T1 % pl.T != 0) break;
+                pl.RS1 = C * pl.T1 + ROW_PAD;
+                pl.epi_batch = pl.T1 > 32 ? pl.T1 : 32;
+                pl.n_tiles1 = (int)((N + pl.T1 - 1) / pl.T1);
+            }
+            act_bytes = hmax * pl.RS1 * 4;
+            ycache_bytes = 2 * sp.n_yrows * pl.epi_batch * 4;
+            slots_bytes = sp.n_slots * 32 * 4;
+            wbuf_bytes = nw * pl.T1 * 4;
+            wslots_bytes = sp.wl > 0 ? sp.n_slots * pl.ntc1 * 4 : 0;
+            const int fixed = act_bytes + small_bytes + ycache_bytes + slots_bytes + misc_bytes + wbuf_bytes + wslots_bytes +
+                              (prog_len + prog_w_len) * 16;
+            // 128-thread forward CTAs share one service warp between weight loading and the residual program -> resident only
+            ns = pick_stages(fixed, pl.chunks_fwd, pl.ntc1 == 128 ? 3 : 1, pl.ntc1 == 128);
+        }
         if (ns < 0) return fail(-2, "forward kernel does not fit in shared memory");
         pl.n_stage = ns;
         pl.resident_fwd = ns >= pl.chunks_fwd;

@@ -104,6 +104,34 @@ def pad_scheme(n1, n2):
     return best
 
 
+class _PinnedStage:
+    """Page-locked staging buffers for host coordinate columns, DOUBLE-BUFFERED and fenced with CUDA events: the host copy
+    into a pinned buffer waits for the event recorded after the previous H2D copy OUT of that buffer, so a batch can never
+    be overwritten while its asynchronous copy is still queued behind a running graph replay (n_batches > 1 per epoch
+    phase with a single sync per phase)."""
+    DEPTH = 2
+
+    def __init__(self, n_cols, n, device):
+        self.bufs = [[torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(n_cols)] for _ in range(self.DEPTH)]
+        self.done = [[None] * n_cols for _ in range(self.DEPTH)]
+        self.turn = [0] * n_cols
+        self.device = device
+
+    def copy_in(self, col, dst, src):
+        k = self.turn[col]
+        self.turn[col] = (k + 1) % self.DEPTH
+        ev = self.done[k][col]
+        if ev is not None:
+            ev.synchronize()                  # the copy that last read this pinned buffer has completed
+        pin = self.bufs[k][col]
+        # single-threaded host copy (+ dtype conversion): torch's parallel CPU copy costs milliseconds on many-core hosts
+        np.copyto(pin.numpy(), src.numpy(), casting="same_kind")
+        dst.copy_(pin, non_blocking=True)
+        if ev is None:
+            ev = self.done[k][col] = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+
+
 class FusedProblem:
     """Device state for one (nets, conditions, diff_eqs): spec, programs, flat parameter/gradient storage, workspace."""
 
@@ -441,14 +469,31 @@ class FusedProblem:
         return info
 
     # ---- CUDA-graph replay of a whole residual+gradient evaluation -----------------------------------------------------
-    def _graph_state(self, n, n_global, train):
-        key = (int(n), int(n_global), bool(train))
+    GRAPH_CACHE_SIZE = 8          # captured graphs kept (LRU); generators whose batch size changes every call would
+    GRAPH_MAX_DISTINCT = 32       # otherwise re-capture forever: beyond this many distinct sizes new sizes run un-graphed
+
+    def _graph_lookup(self, key):
         st = self._graphs.get(key)
         if st is not None:
+            self._graphs[key] = self._graphs.pop(key)      # most recently used last
+        return st
+
+    def _graph_store(self, key, st):
+        self._graphs[key] = st
+        self._graph_keys_seen = getattr(self, "_graph_keys_seen", 0) + 1
+        while len(self._graphs) > self.GRAPH_CACHE_SIZE:    # evict the least recently used graph and its static / pinned buffers
+            self._graphs.pop(next(iter(self._graphs)))
+
+    def _graph_state(self, n, n_global, train):
+        key = (int(n), int(n_global), bool(train))
+        st = self._graph_lookup(key)
+        if st is not None:
             return st
+        if getattr(self, "_graph_keys_seen", 0) >= self.GRAPH_MAX_DISTINCT:
+            return None                                    # ever-changing batch sizes: plain launches from here on
         dev = self.device
         static = [torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(self.n_coords)]
-        pinned = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(self.n_coords)]
+        stage = _PinnedStage(self.n_coords, n, dev)
 
         def body():
             if train:
@@ -467,9 +512,21 @@ class FusedProblem:
             body()
         torch.cuda.synchronize(dev)
         self.gradbuf.copy_(keep)
-        st = (graph, static, pinned)
-        self._graphs[key] = st
+        st = (graph, static, stage)
+        self._graph_store(key, st)
         return st
+
+    @staticmethod
+    def _stage_coords(static, stage, coords):
+        """Host or device coordinate columns -> the static device buffers a captured graph reads."""
+        for i, (dst, src) in enumerate(zip(static, coords)):
+            src = src.detach().reshape(-1)
+            if src.device.type != "cpu":
+                dst.copy_(src)
+            elif src.is_pinned() and src.dtype == torch.float32 and src.is_contiguous():
+                dst.copy_(src, non_blocking=True)     # already page-locked: DMA straight from the caller's buffer
+            else:
+                stage.copy_in(i, dst, src)
 
     def residual_grad_graphed(self, coords, n_global=None, train=True):
         """Same contract as :meth:`residual_grad` with ``sumsq_out=self.sumsq`` (``grad`` and ``sumsq`` ACCUMULATE; zero
@@ -477,16 +534,17 @@ class FusedProblem:
         ``coords`` may be host tensors (staged through persistent pinned buffers) or device tensors.
         ``train=False`` replays the validation path (sum of squared residuals only)."""
         n = coords[0].numel()
-        graph, static, pinned = self._graph_state(n, n if n_global is None else n_global, train)
-        for dst, pin, src in zip(static, pinned, coords):
-            src = src.detach().reshape(-1)
-            if src.device.type != "cpu":
-                dst.copy_(src)
-            elif src.is_pinned() and src.dtype == torch.float32 and src.is_contiguous():
-                dst.copy_(src, non_blocking=True)     # already page-locked: DMA straight from the caller's buffer
-            else:                                     # single-threaded host copy (+ dtype conversion) into the pinned
-                np.copyto(pin.numpy(), src.numpy(), casting="same_kind")   # stage: torch's parallel CPU copy costs
-                dst.copy_(pin, non_blocking=True)                          # milliseconds on many-core hosts
+        n_glob = n if n_global is None else n_global
+        st = self._graph_state(n, n_glob, train)
+        if st is None:                                  # graph cache exhausted (see GRAPH_MAX_DISTINCT): eager launches
+            dev_coords = [c.detach().reshape(-1).to(self.device, torch.float32) for c in coords]
+            if train:
+                self.residual_grad(dev_coords, n_global=n_glob, sumsq_out=self.sumsq)
+            else:
+                self.forward(dev_coords, want_u=False, want_residual=False, want_sumsq=True)   # like the graphed body
+            return self.sumsq
+        graph, static, stage = st
+        self._stage_coords(static, stage, coords)
         graph.replay()
         self.kernel_launches += 5 if train else 3
         return self.sumsq
@@ -501,11 +559,11 @@ class FusedProblem:
         n = coords[0].numel()
         n_glob = n if n_global is None else n_global
         key = ("step", int(n), int(n_glob), id(optimizer))
-        st = self._graphs.get(key)
+        st = self._graph_lookup(key)
         if st is None:
             dev = self.device
             static = [torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(self.n_coords)]
-            pinned = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(self.n_coords)]
+            stage = _PinnedStage(self.n_coords, n, dev)
 
             def body():
                 self.gradbuf.zero_()
@@ -524,19 +582,11 @@ class FusedProblem:
             torch.cuda.synchronize(dev)
             for dst, src in zip((self.theta, self.gradbuf, optimizer._m, optimizer._v, optimizer._t_dev), saved):
                 dst.copy_(src)               # neither the warm-up nor the capture may count as a step
-            st = (graph, static, pinned)
-            self._graphs[key] = st
-        graph, static, pinned = st
+            st = (graph, static, stage)
+            self._graph_store(key, st)
+        graph, static, stage = st
         optimizer.sync_hyperparameters()
-        for dst, pin, src in zip(static, pinned, coords):
-            src = src.detach().reshape(-1)
-            if src.device.type != "cpu":
-                dst.copy_(src)
-            elif src.is_pinned() and src.dtype == torch.float32 and src.is_contiguous():
-                dst.copy_(src, non_blocking=True)
-            else:
-                np.copyto(pin.numpy(), src.numpy(), casting="same_kind")
-                dst.copy_(pin, non_blocking=True)
+        self._stage_coords(static, stage, coords)
         graph.replay()
         optimizer._t += 1
         self.kernel_launches += 5

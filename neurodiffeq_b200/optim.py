@@ -88,3 +88,22 @@ class FlatAdam(torch.optim.Optimizer):
 
     def zero_grad(self, set_to_none=False):
         self._grad.zero_()
+
+    # ---- checkpointing: the moments and the step count live outside ``self.state`` (flat buffers) ------------------------
+    def state_dict(self):
+        d = super().state_dict()
+        d["flat_adam"] = {"step": int(self._t), "exp_avg": self._m.detach().clone(), "exp_avg_sq": self._v.detach().clone()}
+        return d
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flat = state_dict.pop("flat_adam", None)
+        super().load_state_dict(state_dict)
+        if flat is not None:
+            self._t = int(flat["step"])
+            self._m.copy_(flat["exp_avg"].to(self._m.device, self._m.dtype))
+            self._v.copy_(flat["exp_avg_sq"].to(self._v.device, self._v.dtype))
+            if self.capturable:
+                self._t_dev.fill_(float(self._t))
+                self._lr_host = None                 # force the next sync to push the restored learning rate
+                self.sync_hyperparameters()

@@ -15,6 +15,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a CUDA device: skip (not fail) them where none is visible (the CPU container)."""
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:   # noqa: BLE001
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device visible")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name_prefix):
     """Golden vectors produced by the unmodified reference (tests/golden/generate.py)."""
     for fn in sorted(os.listdir(GOLDEN_DIR)):

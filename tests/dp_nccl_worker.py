@@ -1,0 +1,71 @@
+"""torchrun worker of tests/test_round2_gpu.py::test_two_nccl_ranks_reproduce_the_single_gpu_gradient (one rank per GPU).
+
+  python -m torch.distributed.run --nproc-per-node 2 ... tests/dp_nccl_worker.py <workload> <out.json>
+
+Every rank (a) evaluates the WHOLE batch alone, (b) evaluates its slice with the global loss scale and all-reduces the flat
+[grad | sum r^2] buffer over NCCL, (c) runs Solver.fit under data parallelism; rank 0 writes the deviations."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    key, out = sys.argv[1], sys.argv[2]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import workloads
+    from helpers import build_fused, get_params
+    from neurodiffeq_b200.parallel import shard_bounds, all_reduce_gradbuf
+    from test_solvers_gpu import make_solver
+
+    wl, nets, conds, fp = build_fused(key, seed=4)              # same seed: replicated parameters
+    n = 6001                                                    # odd: unequal shards
+    coords = [torch.from_numpy(c).cuda() for c in workloads.sample_coords(wl, n, seed=8)]
+    fp.gradbuf.zero_()
+    fp.residual_grad(coords, n_global=n, sumsq_out=fp.sumsq)
+    full = fp.gradbuf.clone()
+    lo, hi = shard_bounds(n, rank, world)
+    fp.gradbuf.zero_()
+    fp.residual_grad([c[lo:hi].contiguous() for c in coords], n_global=n, sumsq_out=fp.sumsq)
+    all_reduce_gradbuf(fp.gradbuf, dist)
+    torch.cuda.synchronize()
+    grad_rel = float((fp.gradbuf[:-1] - full[:-1]).norm() / full[:-1].norm())
+    sumsq_rel = float(abs(fp.gradbuf[-1] - full[-1]) / full[-1])
+
+    # Solver.fit in lock-step: the ranks end with identical parameters, equal to a single-process run of the same problem
+    wl, solver, snets, coords_np = make_solver(key, 3001)
+    assert solver._dist is not None
+    solver.fit(4, tqdm_file=None)
+    theta = torch.cat([torch.as_tensor(p).reshape(-1) for p in get_params(snets)]).cuda()
+    gathered = [torch.empty_like(theta) for _ in range(world)]
+    dist.all_gather(gathered, theta)
+    identical = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+    wl, single, nets1, _ = make_solver(key, 3001, data_parallel=False)
+    single.fit(4, tqdm_file=None)
+    theta1 = torch.cat([torch.as_tensor(p).reshape(-1) for p in get_params(nets1)]).cuda()
+    fit_rel = float((theta - theta1).norm() / theta1.norm())
+    losses_rel = float(np.max(np.abs(np.array(solver.metrics_history["train_loss"]) / np.array(single.metrics_history["train_loss"]) - 1.0)))
+    dist.barrier()
+    if rank == 0:
+        with open(out, "w") as f:
+            json.dump({"workload": key, "world": world, "points": n, "grad_rel": grad_rel, "sumsq_rel": sumsq_rel,
+                       "fit_theta_rel": fit_rel, "fit_loss_rel": losses_rel, "fit_ranks_identical": identical}, f)
+        print("dp_nccl_worker", key, "grad_rel", grad_rel, "sumsq_rel", sumsq_rel, "fit_theta_rel", fit_rel,
+              "fit_loss_rel", losses_rel, "identical", identical, flush=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)     # skip the NCCL teardown (can block after captured collectives)
+
+
+if __name__ == "__main__":
+    main()

@@ -106,3 +106,52 @@ def assert_parity(got_u, got_r, got_loss, got_grads, ref, label=""):
     if got_grads is not None:
         e = rel_l2(got_grads, ref["grads"])
         assert e <= TOL_GRAD, f"{label} grad rel-L2 {e:.3e}"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference trainings on the CPU oracle (autograd, float64) shared by the CPU (stand-in engine) and GPU solver tests
+# ----------------------------------------------------------------------------------------------------------------------
+def oracle_training_custom(key, params, coords_np, epochs, loss_of, lr=1e-3):
+    """Adam on ``loss_of(residual, funcs, coords)`` (reference solvers.py:369-395 with a custom criterion / additional_loss)."""
+    from oracle import reference_port as oracle
+    wl = workloads.build(oracle.NAMESPACE, key)
+    nets, conds = wl.make_nets(), wl.make_conditions()
+    oracle.load_params(nets, params, dtype=torch.float64)
+    mods = oracle.distinct_modules(nets)
+    opt = torch.optim.Adam([p for m in mods for p in m.parameters()], lr=lr)
+    losses = []
+    for _ in range(epochs):
+        opt.zero_grad()
+        cols = [torch.as_tensor(c, dtype=torch.float64).reshape(-1, 1).requires_grad_(True) for c in coords_np]
+        funcs = [c.enforce(n, *cols) for n, c in zip(nets, conds)]
+        res = torch.cat(workloads.bundle_eq_wrapper(wl)(*funcs, *cols), dim=1)
+        loss = loss_of(res, funcs, cols)
+        loss.backward()
+        losses.append(float(loss.detach()))
+        opt.step()
+    return losses, [p.detach().numpy().copy() for m in mods for p in m.parameters()]
+
+
+def oracle_training_lbfgs(key, params, coords_np, epochs, **lbfgs_kw):
+    """One ``LBFGS.step(closure)`` per epoch on a fixed batch (reference solvers.py:398-400); the recorded loss is the one
+    of the closure's last evaluation."""
+    from oracle import reference_port as oracle
+    owl = workloads.build(oracle.NAMESPACE, key)
+    onets, oconds = owl.make_nets(), owl.make_conditions()
+    oracle.load_params(onets, params, dtype=torch.float64)
+    oparams = [p for m in oracle.distinct_modules(onets) for p in m.parameters()]
+    oopt = torch.optim.LBFGS(oparams, **lbfgs_kw)
+    ref_losses = []
+    for _ in range(epochs):
+        last = {}
+
+        def closure():
+            oopt.zero_grad()
+            cols = [torch.as_tensor(c, dtype=torch.float64).reshape(-1, 1).requires_grad_(True) for c in coords_np]
+            _, _, loss = oracle.closure(onets, oconds, owl.diff_eqs, cols)
+            last["loss"] = float(loss.detach())
+            return loss
+
+        oopt.step(closure)
+        ref_losses.append(last["loss"])
+    return ref_losses, [p.detach().numpy().copy() for p in oparams]

@@ -67,17 +67,9 @@ def test_boundary_values_are_satisfied():
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# Features added after the last GPU call of round 1 (CPU-verified against the reference): EnsembleCondition (x7), IBVP1D
-# with Neumann data on both ends through a shared jet direction (x8), Resnet (x9), 'h1 semi', function-dependent losses.
-# They run with PINNJET_TEST_UNVALIDATED=1 until a GPU run has confirmed them.
+# EnsembleCondition (x7), IBVP1D with Neumann data on both ends through a shared jet direction (x8), Resnet (x9), 'h1 semi'
+# and function-dependent losses: confirmed on a B200 in round 2 (profiles/r02/pytest_gpu_call1.log), always on since.
 # ----------------------------------------------------------------------------------------------------------------------
-import os  # noqa: E402
-
-unvalidated = pytest.mark.skipif(os.environ.get("PINNJET_TEST_UNVALIDATED") != "1",
-                                 reason="not yet run on a GPU; set PINNJET_TEST_UNVALIDATED=1")
-
-
-@unvalidated
 @pytest.mark.parametrize("key", ["x7", "x8", "x9"])
 def test_later_extension_workloads_match_reference_golden(key):
     wl0 = workloads.build(product_namespace(), key)
@@ -88,7 +80,6 @@ def test_later_extension_workloads_match_reference_golden(key):
     assert_parity(None, r2, loss_train, None, gold, label=f"{key} golden(train fwd)")
 
 
-@unvalidated
 @pytest.mark.parametrize("key", ["x7", "x8", "x9"])
 def test_later_extension_workloads_fit_tracks_oracle_adam(key):
     n, epochs = 1100, 5
@@ -101,7 +92,6 @@ def test_later_extension_workloads_fit_tracks_oracle_adam(key):
         np.testing.assert_allclose(a, b, rtol=2e-3, atol=2e-5)
 
 
-@unvalidated
 def test_function_dependent_loss_and_h1_semi_on_the_gpu():
     from test_losses_gpu import oracle_training_with_loss
 

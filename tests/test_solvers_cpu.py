@@ -8,7 +8,7 @@ import torch
 
 import workloads
 from cpu_engine import CpuFusedProblem
-from helpers import get_params
+from helpers import get_params, oracle_training_custom, oracle_training_lbfgs
 from test_solvers_gpu import make_solver, oracle_training
 from test_losses_gpu import oracle_training_with_loss
 
@@ -120,7 +120,6 @@ def test_ensemble_solution_is_a_block_cpu():
 def test_lbfgs_closure_mode_cpu():
     """LBFGS (reference solvers.py:398-400): one step(closure) per batch; the closure re-evaluates loss and gradient.
     Same optimizer, same closure semantics on the oracle (autograd) -> same parameters."""
-    from oracle import reference_port as oracle
     key, n, epochs = "x6", 60, 3
     wl = workloads.build(__import__("helpers").product_namespace(), key)
     torch.manual_seed(0)
@@ -135,48 +134,11 @@ def test_lbfgs_closure_mode_cpu():
                          n_batches_valid=1, optimizer=opt)
     solver.fit(epochs, tqdm_file=None)
 
-    owl = workloads.build(oracle.NAMESPACE, key)
-    onets, oconds = owl.make_nets(), owl.make_conditions()
-    oracle.load_params(onets, params0, dtype=torch.float64)
-    oparams = [p for m in oracle.distinct_modules(onets) for p in m.parameters()]
-    oopt = torch.optim.LBFGS(oparams, lr=0.5, max_iter=4, history_size=5)
-    ref_losses = []
-    for _ in range(epochs):
-        last = {}
-
-        def closure():
-            oopt.zero_grad()
-            cols = [torch.as_tensor(c, dtype=torch.float64).reshape(-1, 1).requires_grad_(True) for c in coords_np]
-            _, _, loss = oracle.closure(onets, oconds, owl.diff_eqs, cols)
-            last["loss"] = float(loss.detach())
-            return loss
-
-        oopt.step(closure)
-        ref_losses.append(last["loss"])
+    ref_losses, ref_params = oracle_training_lbfgs(key, params0, coords_np, epochs, lr=0.5, max_iter=4, history_size=5)
     np.testing.assert_allclose(solver.metrics_history["train_loss"], ref_losses, rtol=1e-5)
-    for a, b in zip(get_params(nets), [p.detach().numpy() for p in oparams]):
+    for a, b in zip(get_params(nets), ref_params):
         np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-8)
     assert len(solver.metrics_history["valid_loss"]) == epochs
-
-
-def _oracle_training_custom(key, params, coords_np, epochs, loss_of):
-    from oracle import reference_port as oracle
-    wl = workloads.build(oracle.NAMESPACE, key)
-    nets, conds = wl.make_nets(), wl.make_conditions()
-    oracle.load_params(nets, params, dtype=torch.float64)
-    mods = oracle.distinct_modules(nets)
-    opt = torch.optim.Adam([p for m in mods for p in m.parameters()], lr=1e-3)
-    losses = []
-    for _ in range(epochs):
-        opt.zero_grad()
-        cols = [torch.as_tensor(c, dtype=torch.float64).reshape(-1, 1).requires_grad_(True) for c in coords_np]
-        funcs = [c.enforce(n, *cols) for n, c in zip(nets, conds)]
-        res = torch.cat(workloads.bundle_eq_wrapper(wl)(*funcs, *cols), dim=1)
-        loss = loss_of(res, funcs, cols)
-        loss.backward()
-        losses.append(float(loss.detach()))
-        opt.step()
-    return losses, [p.detach().numpy().copy() for m in mods for p in m.parameters()]
 
 
 def test_loss_that_depends_on_the_functions_cpu():
@@ -190,7 +152,7 @@ def test_loss_that_depends_on_the_functions_cpu():
     wl, solver, nets, coords_np = make_solver(key, n, loss_fn=loss_fn)
     params0 = get_params(nets)
     solver.fit(epochs, tqdm_file=None)
-    ref_losses, ref_params = _oracle_training_custom(key, params0, coords_np, epochs, loss_fn)
+    ref_losses, ref_params = oracle_training_custom(key, params0, coords_np, epochs, loss_fn)
     np.testing.assert_allclose(solver.metrics_history["train_loss"], ref_losses, rtol=5e-7)
     for a, b in zip(get_params(nets), ref_params):
         np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-11)
@@ -214,7 +176,7 @@ def test_overridden_additional_loss_cpu():
     params0 = get_params(nets)
     solver = Penalised(wl.diff_eqs, wl.make_conditions(), nets=nets, train_generator=gen, valid_generator=gen, n_batches_valid=1)
     solver.fit(epochs, tqdm_file=None)
-    ref_losses, ref_params = _oracle_training_custom(
+    ref_losses, ref_params = oracle_training_custom(
         key, params0, coords_np, epochs, lambda r, f, x: (r ** 2).mean() + 0.5 * f[0].mean() ** 2)
     np.testing.assert_allclose(solver.metrics_history["train_loss"], ref_losses, rtol=5e-7)
     for a, b in zip(get_params(nets), ref_params):
