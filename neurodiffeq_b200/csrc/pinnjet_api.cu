@@ -68,6 +68,11 @@ static long long round_up_ll(long long v, long long m) { return (v + m - 1) / m 
 constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA on sm_100
 constexpr int LOSS_PART_BYTES = 4096;
 constexpr int PROG_MAX = 1024;
+constexpr int TC_STAGE = 16 * 32 * 20 * 4;   // pinnjet_tc.cuh: TC_STAGE_BYTES
+constexpr int TC_PROG_RESERVE = 8192;   // shared-memory bytes the tensor-core plan sets aside for the programs
+#ifndef PJ_TC_DEFAULT
+#define PJ_TC_DEFAULT 0   // PINNJET_TC when the variable is unset
+#endif
 
 // Weight-ring depth: keep all chunks resident if that still allows `target_occ` CTAs per SM; otherwise stream with as many
 // stages as fit (>= 2), giving up one CTA per SM at a time.  Returns -1 if nothing fits.
@@ -140,23 +145,8 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
         pl.ntc1 = 256;
         pl.T1 = pl.ntc1 * pl.P1 * pl.Q1 / hmax;
     }
-    if (!pl.tc && ((pl.T1 / pl.P1) % 8 != 0 || pl.T1 % pl.T != 0))
+    if ((pl.T1 / pl.P1) % 8 != 0 || pl.T1 % pl.T != 0)
         return fail(-3, "internal: forward tile %d unsupported (backward tile %d)", pl.T1, pl.T);
-    // tensor-core forward path (opt-in: PINNJET_TC=1): every hidden layer exactly 64 wide (padded), 2 or 4 jet channels
-    pl.tc = 0;
-    {
-        const char* env = getenv("PINNJET_TC");
-        const int level = (env && (env[0] == '1' || env[0] == '2') && env[1] == 0) ? env[0] - '0' : 0;   // 2: transposed epilogue
-        bool ok = level > 0 && (C == 2 || C == 4) && hmax == 64;
-        for (int n = 0; ok && n < sp.n_nets; ++n)
-            for (int h = 1; h < sp.net[n].n_linear; ++h) ok = ok && pl.hp[n][h] == 64;
-        if (ok && (256 / C) % pl.T == 0) {
-            pl.tc = level;
-            pl.ntc1 = 256;
-            pl.T1 = 256 / C;
-            pl.P1 = pl.Q1 = 0;
-        }
-    }
     pl.RS1 = C * pl.T1 + ROW_PAD;
     pl.epi_batch = pl.T1 > 32 ? pl.T1 : 32;   // whole tiles; the program warp walks it 32 points at a time
     pl.n_tiles1 = (int)((N + pl.T1 - 1) / pl.T1);
@@ -190,6 +180,7 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
             pl.chunks_fwd += (hi + CHUNK_FLOATS / ho - 1) / (CHUNK_FLOATS / ho);
             pl.chunks_bwd += (ho + CHUNK_FLOATS / hi - 1) / (CHUNK_FLOATS / hi);
         }
+        pl.b_woutimg[n] = big; big += 3 * 16 * 128 / 4;   // three bf16 images [16 x 64] of the output Linear (tensor-core path)
     }
     pl.pack_floats = big;
 
@@ -206,29 +197,79 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
     pl.sgrad_floats = round_up(off, 4);
     pl.sgrad_copies = (pl.T / pl.P) / 8;
 
+    // Tensor-core path (pinnjet_tc.cuh): every hidden layer exactly 64 wide (after padding), at most 8 jet channels, weight
+    // images resident in shared memory.  PINNJET_TC: 0 = off, 1 = forward kernel only (the FFMA reverse kernel reads a
+    // re-laid-out copy of the records: bring-up / isolation mode), 2 = forward and reverse kernel.
+    pl.tc = pl.tc_bwd = 0;
+    pl.tp = 0;
+    pl.seed_T = pl.T;
+    int tc_nhh = 0;
+    {
+        const char* env = getenv("PINNJET_TC");
+        const int level = env ? ((env[0] >= '0' && env[0] <= '2' && env[1] == 0) ? env[0] - '0' : 0) : PJ_TC_DEFAULT;
+        bool ok = level > 0 && C <= 8 && hmax == 64;
+        for (int n = 0; ok && n < sp.n_nets; ++n) {
+            for (int h = 1; h < sp.net[n].n_linear; ++h) ok = ok && pl.hp[n][h] == 64;
+            tc_nhh += sp.net[n].n_linear - 2;
+        }
+        // Resident weight images (24 KB per hidden->hidden Linear) next to the operand images: both kernels must fit.  The
+        // decision may not depend on the program length (only pj_forward* know it): the programs get a fixed reserve.
+        const int small_b = round_up(pl.small_floats * 4, 128), nw_ = sp.n_nets * sp.wl, tp_ = 128 / (C <= 2 ? 2 : (C <= 4 ? 4 : 8));
+        const int k1_need = 2 * 3 * 128 * 128 + TC_STAGE + tc_nhh * 3 * 64 * 128 + sp.n_nets * 3 * 16 * 128 + small_b +
+                            2 * sp.n_yrows * 64 * 4 + 2 * sp.n_slots * 32 * 4 + 256 + 4 * (nw_ + sp.n_coords) * tp_ * 4 +
+                            (sp.wl > 0 ? sp.n_slots * 32 * 4 : 0) + TC_PROG_RESERVE;
+        const int rec_b = 512 * C * (tp_ / 8) * 4;   // one record block: 512 threads x C x UG floats (UG = 16 / CP = TP / 8)
+        const int k2_need = 2 * 3 * 128 * 128 + TC_STAGE + tc_nhh * 3 * 64 * 128 + small_b + rec_b +
+                            round_up(4 * pl.sgrad_floats * 4, 128) + 256;
+        ok = ok && k1_need <= SMEM_LIMIT && (level < 2 || (k2_need <= SMEM_LIMIT && tc_nhh <= 7));
+        if (ok) {
+            const int CP = C <= 2 ? 2 : (C <= 4 ? 4 : 8);
+            pl.tc = 1;
+            pl.tc_bwd = level >= 2 ? 1 : 0;
+            pl.tp = 128 / CP;
+            pl.ntc1 = 512;
+            pl.T1 = pl.tp;
+            pl.P1 = pl.Q1 = 0;
+            int n_hidden = 0;
+            for (int n = 0; n < sp.n_nets; ++n) n_hidden += sp.net[n].n_linear - 1;
+            pl.tc_rec_layer_floats = 512ll * C * (16 / CP);
+            pl.tc_rec_tile_floats = pl.tc_rec_layer_floats * n_hidden;
+            if (pl.tc_bwd) {   // the reverse kernel tiles like the forward kernel; seeds / weights / records are shared as is
+                pl.T = pl.tp;
+                pl.n_tiles = (int)((N + pl.T - 1) / pl.T);
+                pl.seed_T = pl.tp;
+            }
+            pl.RS1 = C * pl.T1 + ROW_PAD;
+            pl.n_tiles1 = (int)((N + pl.T1 - 1) / pl.T1);
+            pl.grid = pl.grid_bwd = pl.n_tiles < sms ? pl.n_tiles : sms;
+        }
+    }
     // ---- shared memory images ----
     const int jet_bytes = hmax * pl.RS * 4;
     const int small_bytes = round_up(pl.small_floats * 4, 128);
     const int misc_bytes = 256;
-    if (pl.tc) {   // K1-TC: A images (3 x 32 KB, 1024-aligned at offset 0) | W images | small | ycache | slots | misc | ...
-        int n_hh = 0;
-        for (int n = 0; n < sp.n_nets; ++n) n_hh += sp.net[n].n_linear - 2;
+    if (pl.tc) {   // K1-TC: A images of two tiles in flight (2 x 3 x 16 KB, 1024-aligned) | staging | W images | small | ...
         const int nw = sp.n_nets * sp.wl;
         int o = 0;
-        pl.k1_act = o; o += 3 * 256 * 128;
-        pl.k1_ring = o; o += n_hh * 3 * 64 * 128 + (pl.tc == 2 ? sp.n_nets * 3 * 16 * 128 : 0);   // + output-layer images
+        pl.k1_act = o; o += 2 * 3 * 128 * 128;
+        pl.k1_stage = o; o += TC_STAGE;
+        pl.k1_ring = o; o += tc_nhh * 3 * 64 * 128 + sp.n_nets * 3 * 16 * 128;   // hidden->hidden images, then output-layer images
         pl.k1_small = o; o += small_bytes;
+        pl.epi_batch = 64;
         pl.k1_ycache = o; o += 2 * sp.n_yrows * pl.epi_batch * 4;
-        pl.k1_slots = o; o += sp.n_slots * 32 * 4;
+        pl.k1_slots = o; o += 2 * sp.n_slots * 32 * 4;                            // two program warps
         pl.k1_misc = o; o += misc_bytes;
-        pl.k1_wbuf = o; o += nw * pl.T1 * 4;
-        pl.k1_wslots = o; o += sp.wl > 0 ? sp.n_slots * 256 * 4 : 0;
+        pl.k1_wbuf = o; o += 4 * (nw + sp.n_coords) * pl.tp * 4;                   // prefetch ring: weights, then coordinates
+        pl.k1_wslots = o; o += sp.wl > 0 ? sp.n_slots * 32 * 4 : 0;
         pl.k1_prog = o; o += prog_len * 16;
         pl.k1_progw = o; o += prog_w_len * 16;
         pl.k1_bytes = o;
         pl.n_stage = 1;
         pl.resident_fwd = 1;
-        if (o > SMEM_LIMIT) return fail(-2, "tensor-core forward kernel does not fit in shared memory (%d B)", o);
+        if ((prog_len + prog_w_len) * 16 > TC_PROG_RESERVE)
+            return fail(-2, "residual program too long for the tensor-core forward kernel (%d + %d instructions); set PINNJET_TC=0",
+                        prog_len, prog_w_len);
+        if (o > SMEM_LIMIT) return fail(-3, "internal: tensor-core forward kernel needs %d B of shared memory", o);
     } else {   // K1: act | ring | small | ycache | slots | misc | prog
         // The forward CTA shape is K1's own business: it depends on the program length (which only pj_forward* know),
         // so nothing the other entry points share (K2 tile, record layout, workspace, packed weights) may depend on it.
@@ -272,7 +313,22 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
         pl.k1_progw = o; o += prog_w_len * 16;
         pl.k1_bytes = o;
     }
-    {   // K2: G | G2 | Zb | ring | small | ybar | sgrad | misc
+    if (pl.tc_bwd) {   // K2-TC: z_bar images | a images (3 x 16 KB each, 1024-aligned) | staging | W images | small | ...
+        int o = 0;
+        pl.k2_g0 = o; o += 3 * 128 * 128;
+        pl.k2_g1 = o; o += 3 * 128 * 128;
+        pl.k2_zb = o; o += TC_STAGE;
+        pl.k2_ring = o; o += tc_nhh * 3 * 64 * 128;
+        pl.k2_small = o; o += small_bytes;
+        pl.k2_ybar = o; o += 512 * C * (pl.tp / 8) * 4;             // record block (bulk-TMA destination, 16-byte aligned)
+        pl.k2_sgrad = o; o += round_up(4 * pl.sgrad_floats * 4, 128);   // one copy per TMEM lane quarter
+        pl.k2_misc = o; o += misc_bytes;
+        pl.k2_bytes = o;
+        pl.n_stage_bwd = 1;
+        pl.resident_bwd = 1;
+        pl.sgrad_copies = 4;
+        if (o > SMEM_LIMIT) return fail(-3, "internal: tensor-core reverse kernel needs %d B of shared memory", o);
+    } else {   // K2: G | G2 | Zb | ring | small | ybar | sgrad | misc
         const int ybar_bytes = round_up(PJ_MAX_NETS * C * pl.T * 4, 128);
         const int sgrad_bytes = round_up(pl.sgrad_floats * pl.sgrad_copies * 4, 128);
         const int fixed = 3 * jet_bytes + small_bytes + ybar_bytes + sgrad_bytes + misc_bytes;
@@ -294,13 +350,14 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
     // ---- persistent grids: resident CTAs per SM x SMs, capped by the number of tiles ----
     {
         const SchemeEntry* e = find_scheme(sp.n1, sp.n2, sp.wl);
-        const int o1 = pl.tc ? 1 : e->occ((pl.ntc1 == 256 && pl.Q1 == 4) ? 3 : 1, pl.ntc1, pl.k1_bytes), o2 = e->occ(2, pl.ntc, pl.k2_bytes);
+        const int o1 = pl.tc ? 1 : e->occ((pl.ntc1 == 256 && pl.Q1 == 4) ? 3 : 1, pl.ntc1, pl.k1_bytes);
+        const int o2 = pl.tc_bwd ? 1 : e->occ(2, pl.ntc, pl.k2_bytes);
         if (o1 < 1 || o2 < 1) return fail(-2, "kernel does not fit on an SM (occupancy %d / %d, smem %d / %d B)", o1, o2,
                                           pl.k1_bytes, pl.k2_bytes);
         pl.grid = pl.n_tiles1 < sms * o1 ? pl.n_tiles1 : sms * o1;
         pl.grid_bwd = pl.n_tiles < sms * o2 ? pl.n_tiles : sms * o2;
         if (pl.grid > 640) pl.grid = 640;   // loss partials live in the first 2.5 KB of the workspace
-        *occ_min = o2;
+        *occ_min = pl.tc_bwd ? 2 : o2;      // (the tensor-core plan does not depend on the CTA shape: accept it at once)
     }
     // ---- workspace ----
     long long zt = 0;
@@ -309,10 +366,11 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
     pl.zj_tile_floats = zt;
     pl.ws_loss = 0;
     pl.ws_zj = LOSS_PART_BYTES;
-    pl.ws_seed = round_up_ll(pl.ws_zj + 4ll * zt * pl.n_tiles, 256);
+    pl.ws_seed = round_up_ll(pl.ws_zj + (pl.tc_bwd ? 0ll : 4ll * zt * pl.n_tiles), 256);
     pl.ws_gpart = round_up_ll(pl.ws_seed + 4ll * sp.n_yrows * pl.T * pl.n_tiles, 256);
     pl.ws_wts = round_up_ll(pl.ws_gpart + 4ll * sp.n_theta * pl.grid_bwd, 256);
-    pl.ws_bytes = round_up_ll(pl.ws_wts + 4ll * sp.n_nets * sp.wl * pl.T * pl.n_tiles, 256);
+    pl.ws_tcrec = round_up_ll(pl.ws_wts + 4ll * sp.n_nets * sp.wl * pl.T * pl.n_tiles, 256);
+    pl.ws_bytes = round_up_ll(pl.ws_tcrec + (pl.tc ? 4ll * pl.tc_rec_tile_floats * pl.n_tiles1 : 0ll), 256);
 
     return 0;
 }
@@ -408,6 +466,20 @@ __global__ void pack_kernel(const __grid_constant__ PackArgs A, const float* __r
         }
         float* bo = pack + pl.s_bout[n];
         for (int o = tid; o < 4; o += nt) bo[o] = (o < fout) ? b[o] : 0.0f;
+        if (hpL == 64) {   // tensor-core B operand of the output Linear: rows = outputs (zero padded to 16), K = hidden unit
+            unsigned char* img = reinterpret_cast<unsigned char*>(pack + pl.b_woutimg[n]);
+            for (int e = tid; e < 16 * 64; e += nt) {
+                const int r = e >> 6, k = e & 63;
+                float v = (r < fout && k < fin) ? W[r * fin + k] : 0.0f;
+                const size_t off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((((k * 2) >> 4) ^ (r & 7)) << 4) +
+                                   ((k * 2) & 15);
+                for (int t = 0; t < 3; ++t) {
+                    const __nv_bfloat16 hb = __float2bfloat16(v);
+                    *reinterpret_cast<__nv_bfloat16*>(img + (size_t)t * 2048 + off) = hb;
+                    v -= __bfloat162float(hb);
+                }
+            }
+        }
     }
 }
 
@@ -498,13 +570,15 @@ static int run_k1(const PjSpec* spec, const int32_t* prog, int32_t prog_len, con
     char* w = static_cast<char*>(ws);
     a.loss_part = reinterpret_cast<float*>(w + a.plan.ws_loss);
     a.dbg = a.loss_part + 640;   // tail of the 4 KB loss-partial block (only written by PJ_TIMING builds)
-    a.zj = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_zj) : nullptr;
+    a.zj = mode == 1 ? reinterpret_cast<float*>(w + (a.plan.tc ? a.plan.ws_tcrec : a.plan.ws_zj)) : nullptr;
+    a.zj_ffma = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_zj) : nullptr;
     a.seeds = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_seed) : nullptr;
     a.wts = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_wts) : nullptr;
     const SchemeEntry* e = find_scheme(spec->n1, spec->n2, spec->wl);
     if (int rc = check_cuda((a.plan.tc ? e->k1tc : e->k1)(a, a.plan.grid, a.plan.k1_bytes, (cudaStream_t)stream), "forward launch")) return rc;
     if (sumsq_out)
-        return check_cuda(launch_loss_finalize(a.loss_part, a.plan.grid, sumsq_out, (cudaStream_t)stream), "loss finalize");
+        return check_cuda(launch_loss_finalize(a.loss_part, a.plan.tc ? 2 * a.plan.grid : a.plan.grid, sumsq_out, (cudaStream_t)stream),
+                          "loss finalize");
     return 0;
 }
 
@@ -537,7 +611,7 @@ int pj_backward(const PjSpec* spec, const float* const* coords, int64_t n_points
     a.pack = theta_pack;
     a.N = n_points;
     char* w = static_cast<char*>(workspace);
-    a.zj = reinterpret_cast<const float*>(w + a.plan.ws_zj);
+    a.zj = reinterpret_cast<const float*>(w + (a.plan.tc_bwd ? a.plan.ws_tcrec : a.plan.ws_zj));
     a.seeds = reinterpret_cast<const float*>(w + a.plan.ws_seed);
     a.gpart = reinterpret_cast<float*>(w + a.plan.ws_gpart);
     a.wts = reinterpret_cast<const float*>(w + a.plan.ws_wts);

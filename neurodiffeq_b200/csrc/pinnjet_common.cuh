@@ -52,7 +52,13 @@ struct Plan {
     long long b_wt[PJ_MAX_NETS][PJ_MAX_LINEAR];   // hidden->hidden Linear l: [in_p][out_p]  (forward B operand)
     long long b_wo[PJ_MAX_NETS][PJ_MAX_LINEAR];   //                          [out_p][in_p]  (adjoint B operand)
     long long b_wimg[PJ_MAX_NETS][PJ_MAX_LINEAR];   // tensor-core path: 3 bf16 split images of W_l, K-major SWIZZLE_128B (float offset)
-    int tc;                              // 1 / 2: K1 runs the hidden-layer GEMMs on tcgen05 (pinnjet_k1tc.cuh / _k1tc2.cuh)
+    long long b_woutimg[PJ_MAX_NETS];    // tensor-core path: 3 bf16 split images [16 x 64] of the output Linear (rows >= n_out zero)
+    int tc;                              // 1: K1 runs the hidden-layer and output GEMMs on tcgen05 (pinnjet_k1tc3.cuh)
+    int tc_bwd;                          // 1: K2 too (pinnjet_k2tc2.cuh); it reads K1-TC's records in place
+    int tp;                              // tensor-core tile: points per 128 GEMM rows (pinnjet_tc.cuh: TcGeo::TP)
+    int seed_T;                          // tile size of the seed / combined-weight layouts K1 writes ( = tp when tc_bwd, else T)
+    long long tc_rec_layer_floats, tc_rec_tile_floats;   // tensor-core record layout [tile][hidden layer][thread][C*UG]
+    long long ws_tcrec;                  // workspace offset (bytes) of those records
     long long pack_floats;
     // ---- small-gradient accumulators in shared memory (float offsets) ----
     int g_w0[PJ_MAX_NETS], g_b[PJ_MAX_NETS][PJ_MAX_LINEAR], g_wl[PJ_MAX_NETS], g_bout[PJ_MAX_NETS], sgrad_floats;
@@ -62,7 +68,7 @@ struct Plan {
     long long zj_tile_floats;
     long long ws_zj, ws_seed, ws_gpart, ws_loss, ws_bytes;
     // ---- shared memory (byte offsets) ----
-    int k1_act, k1_ring, k1_small, k1_ycache, k1_slots, k1_prog, k1_misc, k1_bytes;
+    int k1_act, k1_ring, k1_small, k1_ycache, k1_slots, k1_prog, k1_misc, k1_bytes, k1_stage;
     int k1_wbuf, k1_wslots, k1_progw;    // combined second-order channel: per-point weights, their interpreter state
     long long ws_wts;                    // workspace: weights [tile][n_nets*wl][T] for K2
     int k2_g0, k2_g1, k2_zb, k2_ring, k2_small, k2_ybar, k2_sgrad, k2_misc, k2_bytes;
@@ -83,7 +89,8 @@ struct K1Args {
     const float* rbar;
     float* u_out;
     float* r_out;
-    float* zj;
+    float* zj;                           // z-jet records (tensor-core layout when plan.tc)
+    float* zj_ffma;                      // plan.tc && !plan.tc_bwd: where the re-laid-out copy for the FFMA reverse kernel goes
     float* seeds;
     float* wts;
     float* loss_part;

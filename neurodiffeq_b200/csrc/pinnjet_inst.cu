@@ -1,11 +1,9 @@
 // pinnjet_inst.cu -- one translation unit per jet-channel scheme: compiled with -DPJ_N1=.. -DPJ_N2=.. (see build.py).
 // PJ_N1 = PJ_N2 = -1 builds the scheme-independent helpers (K2b reduce, loss finalize).
+#include "pinnjet_k1.cuh"
 #include "pinnjet_k2.cuh"
-#include "pinnjet_k1tc2.cuh"
-#ifdef PJ_EXPERIMENTAL
-#include <cstdlib>
-#include "pinnjet_k2tc.cuh"   // work in progress: only in libpinnjet_exp.so (build.py --experimental)
-#endif
+#include "pinnjet_k1tc3.cuh"
+#include "pinnjet_k2tc2.cuh"
 
 #ifndef PJ_WL
 #define PJ_WL 0
@@ -97,23 +95,13 @@ cudaError_t PJ_NAME(launch_k1_, PJ_N1, PJ_N2)(const K1Args& a, int grid, int sme
 }
 
 cudaError_t PJ_NAME(launch_k2_, PJ_N1, PJ_N2)(const K2Args& a, int grid, int smem, cudaStream_t s) {
-#ifdef PJ_EXPERIMENTAL
-    if constexpr (kC == 2 || kC == 4) {   // tensor-core reverse kernel, opt-in: PINNJET_TC_BWD=1
-        static int use_tc = -1;
-        if (use_tc < 0) {
-            const char* e = getenv("PINNJET_TC_BWD");
-            use_tc = (e && e[0] == '1') ? 1 : 0;
-        }
-        const K2tcLayout lay = k2tc_layout(a.spec, a.plan);
-        if (use_tc && lay.ok) {
-            static int ctc = 0;
-            auto kern = k2tc_backward_kernel<PJ_N1, PJ_N2, PJ_WL>;
-            if (cudaError_t e = configure(kern, ctc)) return e;
-            kern<<<grid, K2T_NCW * 32, lay.bytes, s>>>(a);
-            return cudaGetLastError();
-        }
+    if (a.plan.tc_bwd) {   // tensor-core reverse kernel (pinnjet_k2tc2.cuh)
+        static int ctc = 0;
+        auto kern = k2tc2_backward_kernel<PJ_N1, PJ_N2, PJ_WL>;
+        if (cudaError_t e = configure(kern, ctc)) return e;
+        kern<<<grid, K2T_THREADS, smem, s>>>(a);
+        return cudaGetLastError();
     }
-#endif
     static int c128 = 0, c256 = 0;
     if (a.plan.ntc == 128) {
         auto kern = k2_backward_kernel<128, kMinB2_128, kP, kQ, PJ_N1, PJ_N2, PJ_WL>;
@@ -127,24 +115,20 @@ cudaError_t PJ_NAME(launch_k2_, PJ_N1, PJ_N2)(const K2Args& a, int grid, int sme
     return cudaGetLastError();
 }
 
-// tensor-core forward kernel (2 or 4 jet channels, 64-wide hidden layers); returns cudaErrorNotSupported otherwise
+// tensor-core forward kernel (64-wide hidden layers); without the tensor-core reverse kernel the records are copied into
+// the layout the FFMA reverse kernel reads (bring-up / isolation mode)
 cudaError_t PJ_NAME(launch_k1tc_, PJ_N1, PJ_N2)(const K1Args& a, int grid, int smem, cudaStream_t s) {
-    if constexpr (kC == 2 || kC == 4) {
-        if (a.plan.tc == 2) {   // transposed-epilogue variant (pinnjet_k1tc2.cuh)
-            static int c2 = 0;
-            auto kern2 = k1tc2_forward_kernel<PJ_N1, PJ_N2, PJ_WL>;
-            if (cudaError_t e = configure(kern2, c2)) return e;
-            kern2<<<grid, 576, smem, s>>>(a);
-            return cudaGetLastError();
-        }
-        static int c = 0;
-        auto kern = k1tc_forward_kernel<PJ_N1, PJ_N2, PJ_WL>;
-        if (cudaError_t e = configure(kern, c)) return e;
-        kern<<<grid, 320, smem, s>>>(a);
-        return cudaGetLastError();
-    } else {
-        return cudaErrorNotSupported;
+    static int c = 0;
+    auto kern = k1tc3_forward_kernel<PJ_N1, PJ_N2, PJ_WL>;
+    if (cudaError_t e = configure(kern, c)) return e;
+    kern<<<grid, K1T_THREADS, smem, s>>>(a);
+    if (cudaError_t e = cudaGetLastError()) return e;
+    if (a.mode == 1 && !a.plan.tc_bwd) {
+        int n_hidden = 0;
+        for (int n = 0; n < a.spec.n_nets; ++n) n_hidden += a.spec.net[n].n_linear - 1;
+        tc_relayout_records_kernel<kC><<<a.plan.n_tiles1 * n_hidden, TC_NT, 0, s>>>(a, a.zj, a.zj_ffma);
     }
+    return cudaGetLastError();
 }
 
 // resident CTAs per SM for (kernel, ntc, dynamic smem): which = 1 -> K1, 2 -> K2

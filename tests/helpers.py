@@ -98,7 +98,8 @@ def assert_parity(got_u, got_r, got_loss, got_grads, ref, label=""):
             assert d.max() <= TOL_RESID_MAX_ILL * rms + 1e-6, f"{label} residual max|dr|={d.max():.3e} rms={rms:.3e}"
             if ref.get("residual32") is not None:
                 e32 = np.sqrt(((ref["residual32"].astype(np.float64) - ref["residual"]) ** 2).mean())
-                assert np.sqrt((d ** 2).mean()) <= 4.0 * e32 + 1e-9, f"{label} rms error vs reference-fp32 {e32:.3e}"
+                ours = np.sqrt((d ** 2).mean())
+                assert ours <= 4.0 * e32 + 1e-9, f"{label} rms error {ours:.3e} vs reference-fp32 {e32:.3e}"
         else:
             assert d.max() <= tol, f"{label} residual: max|dr|={d.max():.3e} tol={tol:.3e} rms={rms:.3e}"
     if got_loss is not None:
