@@ -448,20 +448,27 @@ def main():
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
     fp32_peak = n_sms * 128 * 2 * sm_mhz * 1e6 / 1e12       # FFMA lanes x 2 flop x clock under load
+    tc_fwd, tc_bwd = bool(info.get("tc")), bool(info.get("tc_bwd"))
+    k1_name = "k1tc3_forward_kernel" if tc_fwd else "k1_forward_kernel"
+    k2_name = "k2tc2_backward_kernel" if tc_bwd else "k2_backward_kernel"
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed `ncu --set full`
+    # capture of the same kernel variant (profiles/r02/traffic.json names the report it was read from); null if none.
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01", "traffic.json")   # dram__bytes_read+write of K1 from `ncu --set full`
+    tpath = os.path.join(ROOT, "profiles", "r02", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(args.workload, {}).get("k1_dram_bytes")
-    tc_on = os.environ.get("PINNJET_TC", "0") == "1"
+            traffic = json.load(f).get(args.workload, {}).get(k1_name, {}).get("dram_bytes")
     roofline = {
-        "kernel": ("k1tc_forward_kernel" if tc_on else "k1_forward_kernel") + " (forward + jets + residual program)",
+        "kernel": k1_name + " (forward + jets + residual program)",
         "bound": "tensor", "achieved": ach_k1,
         "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach_k1 / bf16_peak, "traffic": traffic,
         "peak_source": f"dense bf16 tensor, {peak_src}",
-        "pipe": ("tcgen05 bf16x3 split (6 MMAs per fp32 product), fp32 TMEM accumulators (PINNJET_TC=1)" if tc_on else
-                 "fp32 FFMA2 on CUDA cores (fp32 parity; the bf16x3 tcgen05 forward kernel is opt-in, PINNJET_TC=1, "
-                 "see DESIGN.md)"),
+        "pipe": ("tcgen05.mma kind::f16, bf16x3 split operands (6 bf16 products per fp32 product, fp32 TMEM accumulators): "
+                 "hidden-layer and output contractions on the tensor pipe; layer 0, activation jets and the residual program "
+                 "on the CUDA cores" if tc_fwd else
+                 "fp32 FFMA2 on CUDA cores (network not eligible for the tensor-core kernels: hidden width != 64, "
+                 "or PINNJET_TC=0)"),
+        "tensor_products_per_fp32_product": 6 if tc_fwd else 0,
         "fp32_ffma_peak": fp32_peak, "frac_of_fp32_ffma_peak": ach_k1 / fp32_peak,
         "algorithmic_flops_per_point": wl.flops_fwdjet, "launch_ms": k1_ms, "launch_ms_min": k1_min,
         # `achieved` counts the CANONICAL jet FLOPs (one channel per needed partial derivative).  When the
@@ -469,7 +476,7 @@ def main():
         # channel instead (forward-Laplacian): fewer channels are executed for the same result.
         "channels_canonical": 1 + fp.tp.scheme.n1 + fp.tp.scheme.n2, "channels_executed": fp.tp.n_channels,
         "executed_flops_per_point": executed_flops(wl, fp.tp),
-        "k2": {"kernel": "k2_backward_kernel + k2_reduce_kernel", "algorithmic_flops_per_point": 2 * wl.flops_fwdjet,
+        "k2": {"kernel": k2_name + " + k2_reduce_kernel", "algorithmic_flops_per_point": 2 * wl.flops_fwdjet,
                "launch_ms": k2_ms, "achieved": 2 * flops_k1 / (k2_ms * 1e-3) / 1e12,
                "frac_of_fp32_ffma_peak": 2 * flops_k1 / (k2_ms * 1e-3) / 1e12 / fp32_peak},
     }

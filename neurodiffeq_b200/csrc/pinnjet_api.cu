@@ -71,7 +71,7 @@ constexpr int PROG_MAX = 1024;
 constexpr int TC_STAGE = 16 * 32 * 20 * 4;   // pinnjet_tc.cuh: TC_STAGE_BYTES
 constexpr int TC_PROG_RESERVE = 8192;   // shared-memory bytes the tensor-core plan sets aside for the programs
 #ifndef PJ_TC_DEFAULT
-#define PJ_TC_DEFAULT 0   // PINNJET_TC when the variable is unset
+#define PJ_TC_DEFAULT 2   // PINNJET_TC when the variable is unset: tensor-core forward and reverse kernels where eligible
 #endif
 
 // Weight-ring depth: keep all chunks resident if that still allows `target_occ` CTAs per SM; otherwise stream with as many
@@ -219,7 +219,8 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
                             2 * sp.n_yrows * 64 * 4 + 2 * sp.n_slots * 32 * 4 + 256 + 4 * (nw_ + sp.n_coords) * tp_ * 4 +
                             (sp.wl > 0 ? sp.n_slots * 32 * 4 : 0) + TC_PROG_RESERVE;
         const int rec_b = 512 * C * (tp_ / 8) * 4;   // one record block: 512 threads x C x UG floats (UG = 16 / CP = TP / 8)
-        const int k2_need = 2 * 3 * 128 * 128 + TC_STAGE + tc_nhh * 3 * 64 * 128 + small_b + rec_b +
+        const int k2_small = round_up((sp.n_nets * PJ_MAX_NETS * 64 + 2 * (sp.n_yrows + nw_ + sp.n_coords) * tp_) * 4, 128);
+        const int k2_need = 2 * 3 * 128 * 128 + TC_STAGE + tc_nhh * 3 * 64 * 128 + k2_small + rec_b +
                             round_up(4 * pl.sgrad_floats * 4, 128) + 256;
         ok = ok && k1_need <= SMEM_LIMIT && (level < 2 || (k2_need <= SMEM_LIMIT && tc_nhh <= 7));
         if (ok) {
@@ -319,7 +320,8 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
         pl.k2_g1 = o; o += 3 * 128 * 128;
         pl.k2_zb = o; o += TC_STAGE;
         pl.k2_ring = o; o += tc_nhh * 3 * 64 * 128;
-        pl.k2_small = o; o += small_bytes;
+        pl.k2_small = o;   // last-Linear rows [net][4][64], then the double-buffered tile info (seeds | weights | coordinates)
+        o += round_up((sp.n_nets * PJ_MAX_NETS * 64 + 2 * (sp.n_yrows + sp.n_nets * sp.wl + sp.n_coords) * pl.tp) * 4, 128);
         pl.k2_ybar = o; o += 512 * C * (pl.tp / 8) * 4;             // record block (bulk-TMA destination, 16-byte aligned)
         pl.k2_sgrad = o; o += round_up(4 * pl.sgrad_floats * 4, 128);   // one copy per TMEM lane quarter
         pl.k2_misc = o; o += misc_bytes;
@@ -526,6 +528,8 @@ int pj_plan_info(const PjSpec* spec, int64_t n_points, int64_t* out, int32_t n_o
         for (int l = 0; l <= PJ_MAX_LINEAR && k < n_out; ++l) out[k++] = pl.hp[n][l];
         for (int l = 0; l < PJ_MAX_LINEAR && k < n_out; ++l) out[k++] = pl.zj_off[n][l];
     }
+    const long long tail[6] = {pl.tc, pl.tc_bwd, pl.tp, pl.ws_tcrec, pl.grid_bwd, pl.n_tiles1};
+    for (int i = 0; i < 6 && k < n_out; ++i) out[k++] = tail[i];
     return 0;
 }
 

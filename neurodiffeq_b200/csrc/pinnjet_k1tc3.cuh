@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(K1T_THREADS, 1) k1tc3_forward_kernel(const __g
             }
             if constexpr (WL > 0) {   // per-point weights of the combined second-order channel (coordinate-only expressions)
                 for (int pt = lane; pt < TP; pt += 32) {
-                    run_program_rt(progw_s, A.prog_w_len, wslots + lane, 32, A.coords, min(base + pt, A.N - 1), A.N, nullptr, 0,
+                    run_program_rt(progw_s, A.prog_w_len, wslots + lane, A.coords, min(base + pt, A.N - 1), A.N, nullptr, 0,
                                    nullptr, 0.0f, nullptr, nullptr, nullptr, TP, wb + pt, TP);
                 }
                 __syncwarp();
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(K1T_THREADS, 1) k1tc3_forward_kernel(const __g
                 float* seed_tile = (train && gidx < ws_points)
                                        ? A.seeds + (gidx / sT) * ((long long)sp.n_yrows * sT) + (gidx % sT) : nullptr;
                 if (gidx < A.N) {
-                    my_sumsq += run_program_rt(prog_s, A.prog_len, my_slots, 32, A.coords, gidx, A.N, yb + bp, K1T_EB, A.rbar,
+                    my_sumsq += run_program_rt(prog_s, A.prog_len, my_slots, A.coords, gidx, A.N, yb + bp, K1T_EB, A.rbar,
                                                A.loss_scale, A.u_out, A.r_out, seed_tile, sT, nullptr, 0);
                 } else if (seed_tile) {
                     for (int r = 0; r < sp.n_yrows; ++r) seed_tile[r * sT] = 0.0f;   // padded points: zero adjoint

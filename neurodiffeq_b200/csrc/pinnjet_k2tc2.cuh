@@ -26,6 +26,9 @@
 namespace pj {
 
 constexpr int K2T_THREADS = TC_NT + 64;   // 576: compute warps, MMA warp, record warp
+#ifndef PJ_WG_FIRST
+#define PJ_WG_FIRST 0                      // first split product of the weight-gradient GEMM (0: all six, 3: the three largest)
+#endif
 
 // a-jet of a hidden layer from its stored record (channel 0 = tanh(z0) for tanh nets, z0 for sin nets; others z-jets)
 template <int N1, int N2, int WL>
@@ -67,7 +70,8 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
     unsigned char* aimg = smem + pl.k2_g1;                        // 3 x 16 KB: a-jets of the layer below
     unsigned char* wimg = smem + pl.k2_ring;                      // forward weight images, [hidden->hidden Linear][3] x 8 KB
     float* stage = reinterpret_cast<float*>(smem + pl.k2_zb);
-    float* small = reinterpret_cast<float*>(smem + pl.k2_small);
+    float* wlo_s = reinterpret_cast<float*>(smem + pl.k2_small);  // [net][output][64] last Linear, out-major; then the tile info:
+    float* tinfo = wlo_s + sp.n_nets * PJ_MAX_NETS * TC_H;        // [2][n_yrows seeds | n_nets*WL weights | n_coords coordinates][TP]
     float* recbuf = reinterpret_cast<float*>(smem + pl.k2_ybar);  // record block of the current step
     float* sgrad = reinterpret_cast<float*>(smem + pl.k2_sgrad);  // [4 quarters][sgrad_floats]
     uint64_t* wfull = reinterpret_cast<uint64_t*>(smem + pl.k2_misc);
@@ -77,7 +81,9 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
     uint64_t* wg_done = wfull + 4;       // weight-gradient MMAs have read ZIMG / AIMG
     uint64_t* rec_full = wfull + 5;      // record block landed
     uint64_t* rec_empty = wfull + 6;     // every compute warp has copied its part (16 warp arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 7);
+    uint64_t* ti_full = wfull + 7;       // [2] seeds / weights / coordinates of a tile staged
+    uint64_t* ti_empty = wfull + 9;      // [2] the tile is finished (16 warp arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 11);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = pl.n_tiles1;
@@ -98,6 +104,10 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
         mbar_init(wg_done, 1);
         mbar_init(rec_full, 1);
         mbar_init(rec_empty, TC_NCW);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&ti_full[b], 1);
+            mbar_init(&ti_empty[b], TC_NCW);
+        }
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -109,7 +119,10 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = tid; i < pl.small_floats; i += K2T_THREADS) small[i] = __ldg(A.pack + i);
+    for (int i = tid; i < sp.n_nets * PJ_MAX_NETS * TC_H; i += K2T_THREADS) {
+        const int n = i / (PJ_MAX_NETS * TC_H), r = i - n * (PJ_MAX_NETS * TC_H);
+        wlo_s[i] = r < sp.net[n].width[sp.net[n].n_linear] * TC_H ? __ldg(A.pack + pl.s_wlo[n] + r) : 0.0f;
+    }
     for (int i = tid; i < 4 * pl.sgrad_floats; i += K2T_THREADS) sgrad[i] = 0.0f;
     for (long long i = tid; i < sp.n_theta; i += K2T_THREADS) gpart[i] = 0.0f;   // parameters no network of the spec owns
     if constexpr (G::CP != C)   // rows of padded channels are never written: they must read as zero in both GEMMs
@@ -165,8 +178,8 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
                     tc_fence_after();
                     TC_MARK(tr, 3 | (h << 5))
                     if (lane == 0) {   // W_bar_l[j][k] += sum_r z_bar_h[r][j] a_{h-1}[r][k]; the accumulator lives across tiles
-                        tc_mma_split6<TC_ROWS / 16, TC_AIMG, 2048, TC_AIMG, 2048>(tmem_base + 64u + (uint32_t)slot * 64u, dz, da,
-                                                                                  IDESC_WG, iter > 0);
+                        tc_mma_split6<TC_ROWS / 16, TC_AIMG, 2048, TC_AIMG, 2048, PJ_WG_FIRST>(tmem_base + 64u + (uint32_t)slot * 64u, dz, da,
+                                                                                               IDESC_WG, iter > 0);
                         tc_commit(wg_done);
                     }
                     __syncwarp();
@@ -181,6 +194,23 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
     if (warp == TC_NCW + 1) {   // ================= record warp: one block per (tile, net, hidden layer), in the order of use ====
         uint32_t ph = 0;
         bool first = true;
+        const int NW = sp.n_nets * WL, ti_rows = sp.n_yrows + NW + sp.n_coords;
+        auto stage_tile_info = [&](int it) {     // seeds, combined-channel weights and coordinates of tile `it` -> tinfo[it & 1]
+            if (it >= 2) mbar_wait(&ti_empty[it & 1], (uint32_t)(((it >> 1) - 1) & 1));
+            const long long t = (long long)blockIdx.x + (long long)it * gridDim.x;
+            float* dst = tinfo + (size_t)(it & 1) * ti_rows * TP;
+            for (int e = lane; e < ti_rows * TP; e += 32) {
+                const int row = e / TP, pt = e - row * TP;
+                float v;
+                if (row < sp.n_yrows) v = __ldg(A.seeds + t * ((long long)sp.n_yrows * TP) + e);
+                else if (row < sp.n_yrows + NW) v = __ldg(A.wts + t * ((long long)NW * TP) + (e - sp.n_yrows * TP));
+                else v = __ldg(A.coords[row - sp.n_yrows - NW] + min(t * TP + pt, A.N - 1));
+                dst[e] = v;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ti_full[it & 1]);
+        };
+        if (my_tiles > 0) stage_tile_info(0);
 #pragma unroll 1
         for (int iter = 0; iter < my_tiles; ++iter) {
             const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
@@ -201,6 +231,8 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
                                      REC_BYTES, rec_full);
                     }
                     __syncwarp();
+                    // one tile ahead, in the idle time after the tile's last block has been requested
+                    if (n == sp.n_nets - 1 && h == 1 && iter + 1 < my_tiles) stage_tile_info(iter + 1);
                 }
                 lidx0 += L;
             }
@@ -243,8 +275,9 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
 
 #pragma unroll 1
     for (int iter = 0; iter < my_tiles; ++iter) {
-        const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
-        const long long gp = min(tile * TP + th.p, A.N - 1);
+        const int NW = sp.n_nets * WL;
+        const float* ti = tinfo + (size_t)(iter & 1) * (sp.n_yrows + NW + sp.n_coords) * TP + th.p;   // this point's column
+        mbar_wait(&ti_full[iter & 1], (uint32_t)((iter >> 1) & 1));
 
 #pragma unroll 1
         for (int n = 0; n < sp.n_nets; ++n) {
@@ -255,16 +288,15 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
             TC_MARK(tr, 1)
             float wq[WLN];
 #pragma unroll
-            for (int d = 0; d < WLN; ++d)
-                wq[d] = WL > 0 ? __ldg(A.wts + tile * ((long long)sp.n_nets * WL * TP) + (n * WL + d) * TP + th.p) : 0.0f;
+            for (int d = 0; d < WLN; ++d) wq[d] = WL > 0 ? ti[(sp.n_yrows + n * WL + d) * TP] : 0.0f;
             // seeds of this thread's point (the 16 threads of a point read the same words)
             float yb_[PJ_MAX_NETS][C];
             {
-                const float* sd = A.seeds + tile * ((long long)sp.n_yrows * TP) + (long long)net.yrow0 * TP + th.p;
+                const float* sd = ti + net.yrow0 * TP;
 #pragma unroll
                 for (int o = 0; o < PJ_MAX_NETS; ++o)
 #pragma unroll
-                    for (int c = 0; c < C; ++c) yb_[o][c] = o < n_out ? __ldg(sd + (o * C + c) * TP) : 0.0f;
+                    for (int c = 0; c < C; ++c) yb_[o][c] = o < n_out ? sd[(o * C + c) * TP] : 0.0f;
             }
 #ifdef PJ_DBG_REC_GLOBAL
             int dbg_l0 = 0;
@@ -277,7 +309,7 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
             // (1) last Linear: a_bar_L = W_out^T y_bar, reverse activation of hidden L, gradients of W_out / b_out / b_L
             float zb[C][UG];                                       // z_bar of the layer just processed (owner layout)
             {
-                const float* wlo = small + pl.s_wlo[n];            // [n_out][64]
+                const float* wlo = wlo_s + n * PJ_MAX_NETS * TC_H;  // [n_out][64]
                 float gwl[PJ_MAX_NETS][UG], gbv[UG];
 #pragma unroll
                 for (int k = 0; k < UG; ++k) {
@@ -407,7 +439,7 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
                 for (int i = 0; i < PJ_MAX_COORDS; ++i)
                     if (i < net.n_in) {
                         const int ci = net.in_coord[i];
-                        const float x = __ldg(A.coords[ci] + gp);
+                        const float x = ti[(sp.n_yrows + NW + ci) * TP];
                         float v[UG];
 #pragma unroll
                         for (int k = 0; k < UG; ++k) {
@@ -422,12 +454,15 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
             }
             TC_MARK(tr, 11)
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ti_empty[iter & 1]);           // the tile-info buffer may be refilled
     }
     TC_MARK(tr, 12)
     if (wg_pending) {
         mbar_wait(wg_done, ph_wg);
         ph_wg ^= 1u;
     }
+    TC_MARK(tr, 14)
 
     // ---- this CTA's partial: small gradients (sum of the four quarter copies) from shared memory, hidden->hidden weight
     // gradients from TMEM.  Instances of one module (boundary instances, pinnjet.h) share w_off / b_off: a later instance
@@ -439,6 +474,7 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
 #pragma unroll 1
         for (int n = 0; n < sp.n_nets; ++n) {
             bar_named(9, TC_NT);                                   // shared-memory sums complete / previous net's stores done
+            TC_MARK(tr, 15)
             const PjNet& net = sp.net[n];
             bool shared_w = false;
             for (int m = 0; m < n; ++m) shared_w = shared_w || sp.net[m].w_off[0] == net.w_off[0];
@@ -448,14 +484,22 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
                 const float v = (sgrad[s_idx] + sgrad[SG + s_idx]) + (sgrad[2 * SG + s_idx] + sgrad[3 * SG + s_idx]);
                 if (shared_w) gpart[off] += v; else gpart[off] = v;
             };
+            // (cold code, executed once per CTA: kept small -- it runs at instruction-fetch speed)
+#pragma unroll 1
             for (int e = tid; e < h1 * net.n_in; e += TC_NT) put(net.w_off[0] + e, pl.g_w0[n] + e);
+#pragma unroll 1
             for (int hl = 0; hl < L; ++hl)
+#pragma unroll 1
                 for (int e = tid; e < net.width[hl + 1]; e += TC_NT) put(net.b_off[hl] + e, pl.g_b[n][hl] + e);
+#pragma unroll 1
             for (int e = tid; e < n_out * hL; e += TC_NT) {
                 const int o = e / hL, k = e - o * hL;
                 put(net.w_off[L] + e, pl.g_wl[n] + o * TC_H + k);
             }
+#pragma unroll 1
             for (int e = tid; e < n_out; e += TC_NT) put(net.b_off[L] + e, pl.g_bout[n] + e);
+            TC_MARK(tr, 16)
+#pragma unroll 1
             for (int l = 1; l < L; ++l, ++slot) {   // M = 64 accumulator: row j in lane (j % 16) + 32 * (j / 16)
                 const int width_j = net.width[l + 1], width_k = net.width[l];
                 uint32_t v[16];

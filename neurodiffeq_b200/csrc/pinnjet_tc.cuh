@@ -89,16 +89,17 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 // only the last KSTEPS MMAs run at full magnitude (measured on C4: rms error 5.5e-7 -> see DESIGN.md).  `da0` / `db0` are the
 // descriptors of term 0, K-step 0; the other 23 differ only in the start-address field (bytes >> 4), so every MMA costs
 // two 64-bit adds with immediates.
-template <int KSTEPS, uint32_t A_IMG, uint32_t A_KSTEP, uint32_t B_IMG, uint32_t B_KSTEP>
+// FIRST = 3 issues only the three largest products (a1 b2, a2 b1, a1 b1): ~2^-17 relative instead of ~2^-24.
+template <int KSTEPS, uint32_t A_IMG, uint32_t A_KSTEP, uint32_t B_IMG, uint32_t B_KSTEP, int FIRST = 0>
 __device__ __forceinline__ void tc_mma_split6(uint32_t d_tmem, uint64_t da0, uint64_t db0, uint32_t idesc, bool accumulate_first) {
 #pragma unroll
-    for (int pr = 0; pr < 6; ++pr)
+    for (int pr = FIRST; pr < 6; ++pr)
 #pragma unroll
         for (int k = 0; k < KSTEPS; ++k) {
             constexpr int TA[6] = {0, 2, 1, 0, 1, 0}, TB[6] = {2, 0, 1, 1, 0, 0};
             const uint64_t da = da0 + (uint64_t)((TA[pr] * A_IMG + k * A_KSTEP) >> 4);
             const uint64_t db = db0 + (uint64_t)((TB[pr] * B_IMG + k * B_KSTEP) >> 4);
-            tc_mma(d_tmem, da, db, idesc, (accumulate_first || pr || k) ? 1u : 0u);
+            tc_mma(d_tmem, da, db, idesc, (accumulate_first || pr > FIRST || k) ? 1u : 0u);
         }
 }
 

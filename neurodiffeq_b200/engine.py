@@ -452,7 +452,7 @@ class FusedProblem:
 
     def plan_info(self, n_points):
         """Tiling plan (diagnostics): dict with T, RS, grid, ... plus padded widths and z-jet offsets per net."""
-        n = 19 + PJ_MAX_NETS * (2 * PJ_MAX_LINEAR + 1)
+        n = 19 + PJ_MAX_NETS * (2 * PJ_MAX_LINEAR + 1) + 6
         out = (ctypes.c_int64 * n)()
         with torch.cuda.device(self.device):
             _check(self.lib.pj_plan_info(ctypes.byref(self.spec), n_points, out, n), "pj_plan_info")
@@ -466,6 +466,8 @@ class FusedProblem:
             k += PJ_MAX_LINEAR + 1
             info["zj_off"].append([int(out[k + i]) for i in range(PJ_MAX_LINEAR)])
             k += PJ_MAX_LINEAR
+        for i, name in enumerate(("tc", "tc_bwd", "tc_tile_points", "ws_tcrec", "grid_bwd", "n_tiles_fwd")):
+            info[name] = int(out[k + i])
         return info
 
     # ---- CUDA-graph replay of a whole residual+gradient evaluation -----------------------------------------------------
