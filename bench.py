@@ -313,11 +313,19 @@ def main():
             flush_rd.sum()
     stream = torch.cuda.current_stream()
 
+    reducer = None
+
     def step_body():
         fp.gradbuf.zero_()                                # optimizer.zero_grad() + loss accumulator
         fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq)
         if world > 1:
-            dist.all_reduce(fp.gradbuf)
+            reducer(fp.gradbuf)                           # SUM of [grad | sum r^2] over the ranks (parallel.GradBufReducer)
+
+    if world > 1:
+        from neurodiffeq_b200.parallel import GradBufReducer
+        fp.gradbuf.zero_()
+        fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq)   # allocates the buffers
+        reducer = GradBufReducer(fp.gradbuf, dist)
 
     # warm-up (also sizes buffers, sets kernel attributes)
     for _ in range(max(args.warmup, 3)):
@@ -351,7 +359,7 @@ def main():
             step_body()
 
     launches_per_step = 1 + 5   # gradbuf fill (torch) is not ours; pack, K1, loss-finalize, K2, K2b are
-    ours_per_step = 5
+    ours_per_step = 5 + (1 if (reducer is not None and reducer.mode == "oneshot-nvlink") else 0)
 
     # ---- timed region: K steps, L2 flushed before each, CUDA events per step, max over ranks -------------------------
     if world > 1:
@@ -410,6 +418,31 @@ def main():
     k1_ms, k1_min = time_kernel(k1_only, reps)
     k2_ms, k2_min = time_kernel(k2_only, reps)   # K2 + K2b (z-jets come from the preceding K1, L2 flushed in between)
 
+    # ---- the collective alone (N > 1): our one-shot NVLink kernel and, beside it, the process group's NCCL all-reduce ---
+    collective = None
+    if world > 1:
+        def time_collective(fn, reps=50):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        scratch = fp.gradbuf.clone()
+        collective = {"mode": reducer.mode, "fallback_reason": reducer.why, "bytes": int(scratch.numel() * 4),
+                      "ms_back_to_back": time_collective(lambda: reducer(fp.gradbuf)),
+                      "nccl_all_reduce_ms_back_to_back": time_collective(lambda: dist.all_reduce(scratch)),
+                      "kernel": "pj::allreduce_oneshot_kernel (csrc/pinnjet_comm.cu): peer loads over NVLink, flags with "
+                                "st.release.sys / ld.acquire.sys, sum in rank order" if reducer.mode == "oneshot-nvlink" else
+                                "torch.distributed.all_reduce"}
+
     # ---- e2e: host coordinates in, loss out, through the public call -------------------------------------------------
     def e2e_step():
         # the public call: host coordinates in (staged through pinned buffers, H2D inside), CUDA-graph replay of
@@ -417,7 +450,7 @@ def main():
         fp.gradbuf.zero_()
         fp.residual_grad_graphed(host_coords, n_global=n_global)
         if world > 1:
-            dist.all_reduce(fp.gradbuf)
+            reducer(fp.gradbuf)
         return fp.sumsq.item()   # device -> host read of the step's result
 
     for _ in range(3):
@@ -503,14 +536,14 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl.name}: {wl.solver}, nets {wl.nets_spec}, {n} points/GPU, "
                                    f"residual+grad step = pack+K1+finalize+K2+K2b"
-                                   + (" + NCCL all-reduce of [grad|loss]" if world > 1 else ""),
+                                   + (f" + all-reduce of [grad|loss] ({reducer.mode})" if world > 1 else ""),
                        "points_per_gpu": n, "global_points": n_global, "tile_points": info["T"],
                        "grid": info["grid"], "l2": "flushed before every timed step (256 MiB memset, then 256 MiB streamed read so the lines left are clean)",
                        "cuda_graph": graph is not None, "parallelism": f"dp{world} (points sharded)"},
             "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": ours_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks, "collective": collective,
             "fit": fit, "gpu_autograd_baseline": gpu_cmp,
             "loss": loss, "wall_s_timed_region": t_wall,
             "step_ms_stats": {"min": float(step_ms.min()), "median": float(np.median(step_ms)),

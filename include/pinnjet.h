@@ -125,6 +125,21 @@ int pj_forward_train(const PjSpec* spec, const int32_t* prog_train /*device*/, i
 int pj_backward(const PjSpec* spec, const float* const* coords, int64_t n_points, const float* theta_pack,
                 float* grad_theta /*device, accumulated*/, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- data parallelism: the one collective of the path -------------------------------------------------
+ * Replaces nothing in the reference (single process); replaces the NCCL all-reduce of round 1.  Every rank passes the device
+ * addresses of ONE symmetric buffer per rank (pj_allreduce_bytes(n) bytes each, zero-initialised before the first call,
+ * peer-mapped on every GPU of the node: e.g. torch.distributed._symmetric_memory), its rank, and the flat float buffer
+ * [grad_theta | sum r^2]; out (may alias in) receives the sum over the ranks, bit-identical on every rank.  One launch, no
+ * host synchronisation, CUDA-graph capturable (the epoch counters live in the symmetric buffer).  All ranks must call it
+ * the same number of times with the same n. */
+#define PJ_AR_MAX_RANKS 8
+#define PJ_AR_BLOCKS 8
+#define PJ_AR_FLAG_BYTES (PJ_AR_BLOCKS * PJ_AR_MAX_RANKS * 4)
+#define PJ_AR_HEADER_BYTES 512     /* flags, then one epoch counter per block; the data starts here (16-byte aligned) */
+int64_t pj_allreduce_bytes(int64_t n_floats);
+int pj_allreduce_oneshot(const uint64_t* peer_buffers /*host array [world]*/, int32_t rank, int32_t world,
+                         const float* in /*device*/, float* out /*device*/, int64_t n_floats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

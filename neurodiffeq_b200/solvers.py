@@ -289,6 +289,16 @@ class BaseSolver:
     def compute_func_val(self, net, cond, *coordinates):
         return cond.enforce(net, *coordinates)
 
+    def _reduce_gradbuf(self, fp):
+        """SUM of the flat [grad | sum r^2] buffer over the ranks (parallel.GradBufReducer: one-shot NVLink kernel on the
+        GPUs of a node, the process group's all-reduce otherwise)."""
+        red = getattr(self, "_gradbuf_reducer", None)
+        if red is None or red._for is not fp.gradbuf:
+            from .parallel import GradBufReducer
+            red = self._gradbuf_reducer = GradBufReducer(fp.gradbuf, self._dist)
+            red._for = fp.gradbuf
+        red(fp.gradbuf)
+
     # ---- batches ------------------------------------------------------------------------------------------------------
     def _generate_batch(self, key):
         """Host sampling (stays on the host, north_star).  Returns flat float32 columns, still wherever the generator put
@@ -349,7 +359,7 @@ class BaseSolver:
                 if self._custom_loss is None:
                     fp.residual_grad(coords, n_global=self._n_global, sumsq_out=fp.sumsq, repack=False)
                     if self._dist is not None:
-                        self._dist.all_reduce(fp.gradbuf)    # [grad | sum r^2]: identical on every rank afterwards
+                        self._reduce_gradbuf(fp)              # [grad | sum r^2]: identical on every rank afterwards
                     loss = (fp.sumsq / denom).reshape(()).clone()
                 else:
                     cols = [c.reshape(-1, 1) for c in coords]
@@ -364,7 +374,7 @@ class BaseSolver:
                     loss = loss.detach().reshape(()).to(fp.sumsq.dtype)
                     if self._dist is not None:
                         fp.sumsq.copy_(loss.reshape(1))
-                        self._dist.all_reduce(fp.gradbuf)    # the shares add up to the loss of the whole batch
+                        self._reduce_gradbuf(fp)              # the shares add up to the loss of the whole batch
                         loss = fp.sumsq.reshape(()).clone()
                 self._eval_metrics(coords, metric_values)    # inside the closure, like the reference (:376-378)
                 last["loss"] = loss
@@ -432,7 +442,7 @@ class BaseSolver:
         if self._dist is not None:   # one collective per epoch phase: [grad | loss] summed over the ranks
             fp.sumsq.copy_(loss_acc)
             if key == "train":
-                self._dist.all_reduce(fp.gradbuf)
+                self._reduce_gradbuf(fp)
             else:
                 self._dist.all_reduce(fp.sumsq)
             loss_acc = fp.sumsq.clone()

@@ -24,7 +24,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import workloads
     from helpers import build_fused, get_params
-    from neurodiffeq_b200.parallel import shard_bounds, all_reduce_gradbuf
+    from neurodiffeq_b200.parallel import shard_bounds, all_reduce_gradbuf, GradBufReducer
     from test_solvers_gpu import make_solver
 
     wl, nets, conds, fp = build_fused(key, seed=4)              # same seed: replicated parameters
@@ -36,10 +36,46 @@ def main():
     lo, hi = shard_bounds(n, rank, world)
     fp.gradbuf.zero_()
     fp.residual_grad([c[lo:hi].contiguous() for c in coords], n_global=n, sumsq_out=fp.sumsq)
+    shard = fp.gradbuf.clone()
     all_reduce_gradbuf(fp.gradbuf, dist)
     torch.cuda.synchronize()
     grad_rel = float((fp.gradbuf[:-1] - full[:-1]).norm() / full[:-1].norm())
     sumsq_rel = float(abs(fp.gradbuf[-1] - full[-1]) / full[-1])
+    # the hand-written one-shot NVLink all-reduce: same sum as NCCL's (rank order vs. NCCL's order: fp32 rounding), identical
+    # on every rank, repeatable back to back (epoch / double-buffer protocol) and inside a replayed CUDA graph
+    red = GradBufReducer(shard, dist)
+    oneshot = {"mode": red.mode, "why": red.why}
+    if red.mode == "oneshot-nvlink":
+        work = shard.clone()
+        red2 = red
+        errs, same = [], True
+        for it in range(7):
+            work.copy_(shard * float(it + 1))
+            red2(work)
+            torch.cuda.synchronize()
+            ref = fp.gradbuf * float(it + 1)
+            errs.append(float((work - ref).norm() / ref.norm()))
+            g = [torch.empty_like(work) for _ in range(world)]
+            dist.all_gather(g, work)
+            same = same and all(bool(torch.equal(x, g[0])) for x in g)
+        graph = torch.cuda.CUDAGraph()
+        static = shard.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            red2(static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        dist.barrier()
+        with torch.cuda.graph(graph):
+            red2(static)
+        for it in range(3):
+            static.copy_(shard * float(it + 2))
+            graph.replay()
+            torch.cuda.synchronize()
+            ref = fp.gradbuf * float(it + 2)
+            errs.append(float((static - ref).norm() / ref.norm()))
+        oneshot.update(max_rel_err_vs_nccl=max(errs), ranks_identical=same)
 
     # Solver.fit in lock-step: the ranks end with identical parameters, equal to a single-process run of the same problem
     wl, solver, snets, coords_np = make_solver(key, 3001)
@@ -57,9 +93,9 @@ def main():
     dist.barrier()
     if rank == 0:
         with open(out, "w") as f:
-            json.dump({"workload": key, "world": world, "points": n, "grad_rel": grad_rel, "sumsq_rel": sumsq_rel,
+            json.dump({"workload": key, "world": world, "points": n, "grad_rel": grad_rel, "sumsq_rel": sumsq_rel, "oneshot": oneshot,
                        "fit_theta_rel": fit_rel, "fit_loss_rel": losses_rel, "fit_ranks_identical": identical}, f)
-        print("dp_nccl_worker", key, "grad_rel", grad_rel, "sumsq_rel", sumsq_rel, "fit_theta_rel", fit_rel,
+        print("dp_nccl_worker", key, "oneshot", oneshot, "grad_rel", grad_rel, "sumsq_rel", sumsq_rel, "fit_theta_rel", fit_rel,
               "fit_loss_rel", losses_rel, "identical", identical, flush=True)
     torch.cuda.synchronize()
     dist.barrier()

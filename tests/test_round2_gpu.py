@@ -197,4 +197,6 @@ def test_two_nccl_ranks_reproduce_the_single_gpu_gradient(key, tmp_path):
     import json
     d = json.loads(out.read_text())
     assert d["grad_rel"] <= 1e-6 and d["sumsq_rel"] <= 1e-6, d
+    assert d["oneshot"]["mode"] == "oneshot-nvlink", d            # the product's collective on the GPUs of one node
+    assert d["oneshot"]["max_rel_err_vs_nccl"] <= 1e-6 and d["oneshot"]["ranks_identical"], d
     assert d["fit_theta_rel"] <= 1e-5 and d["fit_ranks_identical"], d
