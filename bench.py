@@ -141,15 +141,20 @@ def run_reference_arm(args):
         return
     wl = workloads.build(__import__("helpers").product_namespace(), args.workload)
     n = args.points or wl.default_n
+    # The reference computes in torch's default dtype, float32 (it never calls set_default_dtype): that is the headline of
+    # this arm.  float64 -- the precision of the parity oracle -- is timed beside it (BASELINE.md §3 asks for both).
     res = cpu_reference_throughput(args.workload, n, seconds=1e9, max_steps=max(args.steps, 1),
-                                   warmup=max(args.warmup, 1))
+                                   warmup=max(args.warmup, 1), dtype=torch.float32)
+    res64 = cpu_reference_throughput(args.workload, n, seconds=1e9, max_steps=max(min(args.steps, 5), 1), warmup=1,
+                                     dtype=torch.float64)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "points/s", "n_gpus": args.gpus,
         "steps": res["steps"], "warmup": max(args.warmup, 1), "ms_per_step": res["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{wl.name} {wl.solver} N={n} (reference closure solvers.py:369-395, CPU port)",
                    "points_per_step": n},
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {**{k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                         "f64": {k: res64[k] for k in ("value", "unit", "cores", "sample")}},
         "e2e": {"value": res["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -526,8 +531,10 @@ def main():
                 gpu_cmp = gpu_autograd_comparator(args.workload, n, dev)
             except Exception as e:
                 gpu_cmp = {"error": f"{type(e).__name__}: {e}"}
-        cpu_base = cpu_reference_throughput(args.workload, n, seconds=args.cpu_seconds)
-        cpu_base = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu32 = cpu_reference_throughput(args.workload, n, seconds=args.cpu_seconds / 2, dtype=torch.float32)
+        cpu64 = cpu_reference_throughput(args.workload, n, seconds=args.cpu_seconds / 2, dtype=torch.float64)
+        cpu_base = {**{k: cpu32[k] for k in ("value", "unit", "cores", "kind", "sample")},   # float32 = the reference's dtype
+                    "f64": {k: cpu64[k] for k in ("value", "unit", "cores", "sample")}}
 
     if rank == 0:
         line = {
