@@ -237,9 +237,11 @@ def _survey_generator(key, n, G):
     raise KeyError(key)
 
 
-def fit_throughput(key, n, epochs, warm=20):
-    """End-to-end ``Solver.fit`` of the product (SURVEY.md §8d "fit() epochs/s"): host sampling of a fresh batch, staging +
-    H2D, K0..K2b (one graph replay), torch Adam, one loss read per epoch; no validation batches (n_batches_valid=0)."""
+def fit_throughput(key, n, epochs, warm=20, device_loop=False):
+    """End-to-end ``Solver.fit`` of the product (SURVEY.md §8d "fit() epochs/s"), no validation batches.  Default loop: host
+    sampling of a fresh batch, staging + H2D, K0..K2b (one graph replay), torch Adam, one loss read per epoch.
+    ``device_loop=True`` (opt-in of the solvers): Philox sampling on the device, K0..K2b, best-parameter bookkeeping and
+    Adam (optim.FlatAdam) replayed as ONE CUDA graph per epoch; the loss history is read back once at the end."""
     from neurodiffeq_b200 import solvers as S, generators as G
     nd = __import__("helpers").product_namespace()
     wl = workloads.build(nd, key)
@@ -247,6 +249,8 @@ def fit_throughput(key, n, epochs, warm=20):
     nets, conds = wl.make_nets(), wl.make_conditions()
     gen = _survey_generator(key, n, G)
     kw = dict(nets=nets, train_generator=gen, valid_generator=gen, n_batches_valid=0)
+    if device_loop:
+        kw["device_loop"] = True
     if wl.solver == "BundleSolver1D":
         kw["eq_param_index"] = wl.eq_param_index
     solver = getattr(S, wl.solver)(wl.diff_eqs, conds, **kw)
@@ -259,8 +263,11 @@ def fit_throughput(key, n, epochs, warm=20):
     hist = solver.metrics_history["train_loss"]
     return {"epochs_per_s": epochs / dt, "points_per_s": epochs * gen.size / dt, "ms_per_epoch": dt / epochs * 1e3,
             "epochs": epochs, "points_per_epoch": int(gen.size), "loss_first": hist[0], "loss_last": hist[-1],
-            "what": f"{wl.solver}.fit: host sampling ({type(gen).__name__}) + H2D + K0..K2b + torch Adam + 1 loss read "
-                    f"per epoch, n_batches_valid=0, wall clock"}
+            "what": (f"{wl.solver}.fit(device_loop=True): one CUDA-graph replay per epoch = Philox sampling "
+                     f"({type(gen).__name__} law) + K0..K2b + best-parameter bookkeeping + FlatAdam; losses read once at "
+                     f"the end; n_batches_valid=0, wall clock" if device_loop else
+                     f"{wl.solver}.fit: host sampling ({type(gen).__name__}) + H2D + K0..K2b + torch Adam + 1 loss read "
+                     f"per epoch, n_batches_valid=0, wall clock")}
 
 
 def executed_flops(wl, tp):
@@ -526,6 +533,10 @@ def main():
                 fit = fit_throughput(args.workload, n, args.fit_epochs)
             except Exception as e:  # the fit leg is a secondary report: never lose the bench line over it
                 fit = {"error": f"{type(e).__name__}: {e}"}
+            try:
+                fit["device_loop"] = fit_throughput(args.workload, n, 5 * args.fit_epochs, device_loop=True)
+            except Exception as e:
+                fit["device_loop"] = {"error": f"{type(e).__name__}: {e}"}
         if not args.no_gpu_comparator:
             try:
                 gpu_cmp = gpu_autograd_comparator(args.workload, n, dev)

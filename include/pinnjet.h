@@ -140,6 +140,40 @@ int64_t pj_allreduce_bytes(int64_t n_floats);
 int pj_allreduce_oneshot(const uint64_t* peer_buffers /*host array [world]*/, int32_t rank, int32_t world,
                          const float* in /*device*/, float* out /*device*/, int64_t n_floats, void* stream);
 
+/* ---- collocation point sampling on the device (opt-in, the host generators stay the default) -----------
+ * Replaces generator.get_examples() (generators.py:107-191 Generator1D, :194-314 Generator2D/3D, :572-655
+ * GeneratorSpherical) + the host->device copy of the batch (solvers.py:340-345).  One law per coordinate (three
+ * consecutive coordinates for the spherical law) as a function of the GLOBAL row index: a rank draws rows
+ * [first, first + n) of the batch.  `state` = two device uint64 words, zero-initialised: {call number, launch ticket};
+ * the kernel advances the call number itself, so a replayed CUDA graph draws fresh points each time. */
+#define PJ_LAW_BASE 0          /* x_i = base[i]                          (fixed nodes)                                   */
+#define PJ_LAW_BASE_NORMAL 1   /* x_i = base[i] + p0 * N(0,1)            ('*-noisy' methods, p0 = noise std)             */
+#define PJ_LAW_UNIFORM 2       /* x_i = p0 + (p1 - p0) * U[0,1)                                                          */
+#define PJ_LAW_SPHERICAL 3     /* (r, theta, phi): p0 = r_min, p1 = r_max, flag 1: r^2 uniform, 0: r uniform             */
+typedef struct PjSampleLaw {
+    int32_t kind, coord, flag, pad_;
+    float p0, p1;
+    int64_t div, mod;                   /* mod > 0: the law is indexed by the NODE (row / div) % mod instead of the row -- axes  */
+                                        /* of a tensor-product ('^') generator: all rows that share a node share its draw        */
+    const float* base;                  /* device, one value per row / node (BASE / BASE_NORMAL), else NULL                      */
+} PjSampleLaw;
+typedef struct PjSampler {
+    uint64_t seed;
+    int32_t n_laws, pad_;
+    PjSampleLaw law[PJ_MAX_COORDS];
+} PjSampler;
+int pj_sample(const PjSampler* sampler, int64_t first, int64_t n, float* const* out /*host array [PJ_MAX_COORDS] of device ptrs*/,
+              uint64_t* state /*device*/, void* stream);
+
+/* ---- Adam on the flat parameter buffer, one launch (opt-in device loop; torch.optim.Adam stays the default) ------------
+ * Replaces optimizer.step() of torch.optim.Adam (solvers.py:182, 396) for amsgrad=False, weight_decay=0.  `state` = three
+ * device doubles {step count t, learning rate, launch ticket (0)}; the kernel advances t itself (graph replay).  With
+ * best_theta != NULL the launch also keeps the best parameters: if *loss < *best_loss, theta BEFORE the update is copied to
+ * best_theta and *best_loss = *loss (solvers.py:411-418). */
+int pj_adam_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double* state /*device*/,
+                 float beta1, float beta2, float eps, const float* loss /*device or NULL*/, float* best_loss, float* best_theta,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,8 @@ def build(force=False, verbose=False, extra_flags=(), lib=None, objdir_name="bui
     os.makedirs(objdir, exist_ok=True)
     jobs = [(os.path.join(objdir, "api.o"), os.path.join(HERE, "pinnjet_api.cu"), list(extra_flags)),
             (os.path.join(objdir, "comm.o"), os.path.join(HERE, "pinnjet_comm.cu"), list(extra_flags)),
+            (os.path.join(objdir, "sample.o"), os.path.join(HERE, "pinnjet_sample.cu"), list(extra_flags)),
+            (os.path.join(objdir, "optim.o"), os.path.join(HERE, "pinnjet_optim.cu"), list(extra_flags)),
             (os.path.join(objdir, "inst_common.o"), os.path.join(HERE, "pinnjet_inst.cu"),
              ["-DPJ_N1=-1", "-DPJ_N2=-1"] + list(extra_flags))]
     for n1, n2, wl in SCHEMES:

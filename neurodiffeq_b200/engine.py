@@ -84,7 +84,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ("pj_abi_version", "pj_last_error", "pj_sizes", "pj_plan_info", "pj_pack", "pj_forward", "pj_forward_train",
-                    "pj_backward", "pj_allreduce_bytes", "pj_allreduce_oneshot")
+                    "pj_backward", "pj_allreduce_bytes", "pj_allreduce_oneshot", "pj_sample", "pj_adam_step")
 
 
 def _check(rc, what):

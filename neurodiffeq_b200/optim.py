@@ -34,9 +34,10 @@ class FlatAdam(torch.optim.Optimizer):
         self._t = 0
         self.capturable = capturable
         if capturable:
-            f64 = dict(dtype=torch.float64, device=theta.device)
-            self._t_dev = torch.zeros((), **f64)
-            self._lr_dev = torch.tensor(float(lr), **f64)
+            # {step count, learning rate, launch ticket of pj_adam_step}: device doubles, so that a captured step replays
+            self._state_dev = torch.zeros(3, dtype=torch.float64, device=theta.device)
+            self._t_dev, self._lr_dev = self._state_dev[0], self._state_dev[1]
+            self._lr_dev.fill_(float(lr))
             self._lr_host = float(lr)
 
     def sync_hyperparameters(self):
@@ -46,6 +47,27 @@ class FlatAdam(torch.optim.Optimizer):
         if self.capturable and lr != self._lr_host:
             self._lr_dev.fill_(lr)
             self._lr_host = lr
+
+    def _step_fused(self, loss=None, best_loss=None, best_theta=None):
+        """The whole update as ONE launch of ``pj_adam_step`` (csrc/pinnjet_optim.cu); with ``best_theta`` the launch also
+        keeps the best parameters seen so far (taken BEFORE the update, like the reference's ``_update_best``)."""
+        import ctypes
+        from .engine import load_library
+        lib = load_library()
+        if not hasattr(lib, "_adam_ready"):
+            vp = ctypes.c_void_p
+            lib.pj_adam_step.argtypes = [vp, vp, vp, vp, ctypes.c_int64, vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, vp, vp,
+                                         vp, vp]
+            lib.pj_adam_step.restype = ctypes.c_int
+            lib._adam_ready = True
+        b1, b2 = self.param_groups[0]["betas"]
+        ptr = lambda t: None if t is None else t.data_ptr()   # noqa: E731
+        rc = lib.pj_adam_step(self._theta.data_ptr(), self._grad.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
+                              self._theta.numel(), self._state_dev.data_ptr(), b1, b2, self.param_groups[0]["eps"], ptr(loss),
+                              ptr(best_loss), ptr(best_theta),
+                              ctypes.c_void_p(torch.cuda.current_stream(self._theta.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"pj_adam_step failed ({rc})")
 
     def _step_on_device(self):
         b1, b2 = self.param_groups[0]["betas"]

@@ -14,6 +14,7 @@ back ONCE per epoch instead of ``.item()`` per batch (:394); the best parameters
 instead of ``deepcopy(nets)`` per improvement (:441).  Unsupported features raise instead of silently falling back.
 """
 import sys
+import types
 import warnings
 from copy import deepcopy
 from inspect import signature
@@ -110,7 +111,7 @@ class BaseSolver:
     def __init__(self, diff_eqs, conditions, nets=None, train_generator=None, valid_generator=None,
                  analytic_solutions=None, optimizer=None, loss_fn=None, n_batches_train=1, n_batches_valid=4,
                  metrics=None, n_input_units=None, n_output_units=None, shuffle=None, batch_size=None,
-                 device=None, data_parallel=True):
+                 device=None, data_parallel=True, device_loop=False):
         if shuffle:
             warnings.warn("param `shuffle` is deprecated and ignored; shuffling should be performed by generators",
                           FutureWarning)
@@ -185,6 +186,13 @@ class BaseSolver:
         if data_parallel and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
             self._dist = torch.distributed
+        # Opt-in: sampling, K0..K2b, the collective, the best-parameter bookkeeping and the Adam step of
+        # an epoch replay as ONE CUDA graph; losses stay on the device and are read back in bulk (see _fit_device_loop).
+        self.device_loop = bool(device_loop)
+        self._device_loop_state = None
+        if self.device_loop and optimizer is None:   # the reference default (Adam, lr 1e-3) on the flat buffers, capturable
+            from .optim import FlatAdam
+            self.optimizer = FlatAdam(self.problem.theta, self.problem.grad, capturable=True)
 
     # ---- hooks for subclasses -----------------------------------------------------------------------------------------
     def _traced_diff_eqs(self, *variables):
@@ -481,6 +489,11 @@ class BaseSolver:
                 loop = tqdm(loop, desc="Training Progress", file=tqdm_file, dynamic_ncols=True)
             except ImportError:
                 pass
+        if self.device_loop:
+            why = self._device_loop_blocker()
+            if why is None:
+                return self._fit_device_loop(loop, callbacks)
+            warnings.warn(f"device_loop=True is not possible here ({why}); running the host loop", RuntimeWarning)
         for local_epoch in loop:
             if self._stop_training:
                 break
@@ -489,6 +502,156 @@ class BaseSolver:
             self.run_valid_epoch()
             for cb in callbacks:
                 cb(self)
+
+    # ---- the device loop (opt-in): one CUDA-graph replay per epoch ------------------------------------------------------
+    def _device_loop_blocker(self):
+        """None if an epoch of this solver can run as one captured graph, else the reason it cannot."""
+        from .device_sampling import describe
+        from .optim import FlatAdam
+        if self._custom_loss is not None:
+            return "the loss needs autograd on the host (custom loss_fn / additional_loss)"
+        if self.metrics_fn:
+            return "metrics are evaluated on the host"
+        if not (isinstance(self.optimizer, FlatAdam) and self.optimizer.capturable):
+            return "the optimizer is not optim.FlatAdam(capturable=True)"
+        if self.n_batches["train"] != 1:
+            return "n_batches_train != 1"
+        if describe(self.generator["train"]) is None:
+            return f"{self.generator['train']!r} has no device sampling law"
+        if self.n_batches["valid"] > 0 and describe(self.generator["valid"]) is None:
+            return f"{self.generator['valid']!r} has no device sampling law"
+        return None
+
+    def _build_device_loop(self):
+        from .device_sampling import DeviceSampler
+        from .parallel import GradBufReducer
+        fp, dev, opt = self.problem, self.device, self.optimizer
+        if not fp.parameters_linked():
+            fp.relink()
+        st = types.SimpleNamespace()
+        world, rank = (self._dist.get_world_size(), self._dist.get_rank()) if self._dist is not None else (1, 0)
+        st.samplers, st.coords, st.bounds = {}, {}, {}
+        for key in ("train", "valid"):
+            if self.n_batches[key] <= 0:
+                continue
+            gen = self.generator[key]
+            st.samplers[key] = DeviceSampler(gen, dev)
+            lo, hi = shard_bounds(gen.size, rank, world)
+            st.bounds[key] = (lo, hi, gen.size)
+            st.coords[key] = [torch.zeros(hi - lo, dtype=torch.float32, device=dev) for _ in range(self.n_coords)]
+        n_valid = self.n_batches["valid"]
+        st.hist = torch.zeros((self.DEVICE_LOOP_CHUNK, 2), dtype=torch.float32, device=dev)   # [epoch in chunk][train, valid]
+        st.idx = torch.zeros(1, dtype=torch.int64, device=dev)
+        st.best_loss = torch.full((1,), float("inf") if self.lowest_loss is None else float(self.lowest_loss),
+                                  dtype=torch.float32, device=dev)
+        st.best_theta = (self.best_nets_theta if self.best_nets_theta is not None else fp.theta).clone()
+        st.valid_acc = torch.zeros(1, dtype=torch.float32, device=dev)
+        lo, hi, n_glob = st.bounds["train"]
+        fp.gradbuf.zero_()
+        fp.residual_grad(st.coords["train"], n_global=n_glob, sumsq_out=fp.sumsq)       # sizes the buffers
+        st.reducer = GradBufReducer(fp.gradbuf, self._dist) if self._dist is not None else None
+
+        def update_best(loss):
+            better = loss < st.best_loss
+            st.best_theta.copy_(torch.where(better, fp.theta, st.best_theta))
+            st.best_loss.copy_(torch.where(better, loss, st.best_loss))
+
+        def body():
+            lo, hi, n_glob = st.bounds["train"]
+            st.samplers["train"].sample_into(st.coords["train"], lo, hi - lo)
+            fp.gradbuf.zero_()
+            fp.residual_grad(st.coords["train"], n_global=n_glob, sumsq_out=fp.sumsq)   # K0, K1, finalize, K2, K2b
+            if st.reducer is not None:
+                st.reducer(fp.gradbuf)
+            train_loss = fp.sumsq / float(n_glob * fp.n_eq)
+            if n_valid == 0:   # lowest loss / best parameters from the training loss, before the optimizer step (reference
+                opt._step_fused(train_loss, st.best_loss, st.best_theta)       # solvers.py:411-412), in the Adam launch
+            else:
+                opt._step_fused()
+            valid_loss = train_loss * 0.0
+            if n_valid > 0:
+                lo, hi, n_glob_v = st.bounds["valid"]
+                st.valid_acc.zero_()
+                fp.pack()                                    # the parameters have just moved
+                for _ in range(n_valid):
+                    st.samplers["valid"].sample_into(st.coords["valid"], lo, hi - lo)
+                    fp.sumsq.zero_()
+                    fp.forward(st.coords["valid"], want_u=False, want_residual=False, want_sumsq=True, repack=False)
+                    st.valid_acc.add_(fp.sumsq)
+                if self._dist is not None:
+                    self._dist.all_reduce(st.valid_acc)
+                valid_loss = st.valid_acc / float(n_glob_v * fp.n_eq * n_valid)
+                update_best(valid_loss)
+            st.hist.index_copy_(0, st.idx, torch.cat([train_loss, valid_loss]).reshape(1, 2))
+            st.idx.add_(1)
+
+        saved = [t.clone() for t in (fp.theta, opt._m, opt._v, opt._state_dev, st.best_loss, st.best_theta)]
+        states = [s.state.clone() for s in st.samplers.values()]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            body()                                           # warm-up: sizes buffers, sets kernel attributes
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if self._dist is not None:
+            self._dist.barrier()
+        st.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(st.graph):
+            body()
+        torch.cuda.synchronize(dev)
+        for dst, src in zip((fp.theta, opt._m, opt._v, opt._state_dev, st.best_loss, st.best_theta), saved):
+            dst.copy_(src)                                   # neither the warm-up nor the capture counts as an epoch
+        for s, old in zip(st.samplers.values(), states):
+            s.state.copy_(old)
+        st.idx.zero_()
+        return st
+
+    DEVICE_LOOP_CHUNK = 1024   # epochs between two bulk reads of the loss history (one device->host copy each)
+
+    def _flush_device_loop(self, st, n_done):
+        """Bulk read of the epochs run since the last flush: histories, lowest loss, best parameters."""
+        if n_done <= 0:
+            return
+        rows = st.hist[:n_done].cpu().numpy()
+        for tr, va in rows:
+            self._update_history(float(tr), "loss", "train")
+            if self.n_batches["valid"] > 0:
+                self._update_history(float(va), "loss", "valid")
+        st.idx.zero_()
+        best = float(st.best_loss.item())
+        if self.lowest_loss is None or best < self.lowest_loss:
+            self.lowest_loss = best
+        if self.best_nets_theta is None:
+            self.best_nets_theta = st.best_theta.clone()
+        else:
+            self.best_nets_theta.copy_(st.best_theta)
+
+    def _fit_device_loop(self, loop, callbacks):
+        st = self._device_loop_state
+        if st is None:
+            st = self._device_loop_state = self._build_device_loop()
+        fp, opt = self.problem, self.optimizer
+        if not fp.parameters_linked():
+            fp.relink()
+        st.best_loss.fill_(float("inf") if self.lowest_loss is None else float(self.lowest_loss))
+        if self.best_nets_theta is not None:
+            st.best_theta.copy_(self.best_nets_theta)
+        pending = 0
+        for local_epoch in loop:
+            if self._stop_training:
+                break
+            self.local_epoch = local_epoch + 1
+            opt.sync_hyperparameters()
+            st.graph.replay()
+            opt._t += 1
+            fp.kernel_launches += 6
+            pending += 1
+            if callbacks or pending == self.DEVICE_LOOP_CHUNK:     # callbacks read histories / lowest_loss every epoch
+                self._flush_device_loop(st, pending)
+                pending = 0
+            for cb in callbacks:
+                cb(self)
+        self._flush_device_loop(st, pending)
 
     # ---- solutions / residuals ----------------------------------------------------------------------------------------
     def _solution_class(self):

@@ -38,6 +38,19 @@ def test_ctypes_struct_layout_matches_c(tmp_path):
     assert (o_woff, o_yrow) == (engine.PjNet.w_off.offset, engine.PjNet.yrow0.offset)
 
 
+def test_sampler_struct_layout_matches_c(tmp_path):
+    from neurodiffeq_b200 import device_sampling as ds
+    src = tmp_path / "sz2.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pinnjet.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", '
+                   'sizeof(PjSampleLaw), sizeof(PjSampler), offsetof(PjSampleLaw, div), offsetof(PjSampleLaw, base), '
+                   'offsetof(PjSampler, law));return 0;}\n')
+    exe = tmp_path / "sz2"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    a, b, o_p0, o_base, o_law = map(int, subprocess.check_output([str(exe)]).split())
+    assert (a, b) == (ctypes.sizeof(ds.PjSampleLaw), ctypes.sizeof(ds.PjSampler))
+    assert (o_p0, o_base, o_law) == (ds.PjSampleLaw.div.offset, ds.PjSampleLaw.base.offset, ds.PjSampler.law.offset)
+
+
 def test_no_gpu_means_loud_failure():
     import torch
     import pytest
