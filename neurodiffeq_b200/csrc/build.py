@@ -70,12 +70,6 @@ def build(force=False, verbose=False, extra_flags=(), lib=None, objdir_name="bui
     return lib
 
 
-def build_experimental():
-    """libpinnjet_exp.so: the product kernels plus work-in-progress ones (pinnjet_k2tc.cuh); select with PINNJET_LIB."""
-    return build(force=True, extra_flags=["-DPJ_EXPERIMENTAL=1"], lib=os.path.join(HERE, "libpinnjet_exp.so"),
-                 objdir_name="build_exp")
-
-
 def build_timing():
     return build(force=True, extra_flags=["-DPJ_TIMING=1", "-rdc=false"], lib=LIB_TIMING, objdir_name="build_timing")
 
@@ -83,7 +77,5 @@ def build_timing():
 if __name__ == "__main__":
     if "--timing" in sys.argv:
         print(build_timing())
-    elif "--experimental" in sys.argv:
-        print(build_experimental())
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
