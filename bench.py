@@ -251,6 +251,7 @@ def fit_throughput(key, n, epochs, warm=20, device_loop=False):
     kw = dict(nets=nets, train_generator=gen, valid_generator=gen, n_batches_valid=0)
     if device_loop:
         kw["device_loop"] = True
+    kw["jit"] = os.environ.get("PINNJET_JIT", "1") != "0"
     if wl.solver == "BundleSolver1D":
         kw["eq_param_index"] = wl.eq_param_index
     solver = getattr(S, wl.solver)(wl.diff_eqs, conds, **kw)
@@ -325,6 +326,7 @@ def main():
             flush_rd.sum()
     stream = torch.cuda.current_stream()
 
+    jit_on = fp.enable_jit() if os.environ.get("PINNJET_JIT", "1") != "0" else False   # specialised forward kernel (jit.py)
     reducer = None
 
     def step_body():
@@ -562,6 +564,9 @@ def main():
                     "d2h_bytes_per_step": 4},
             "gpu_launches": ours_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks, "collective": collective,
+            "specialised_forward_kernel": {"in_use": bool(jit_on), "why_not": "" if jit_on else fp.jit_reason,
+                                           "what": "residual programs compiled into k1tc3 (neurodiffeq_b200/jit.py, nvcc, "
+                                                   "cached); PINNJET_JIT=0 keeps the in-kernel interpreter"},
             "fit": fit, "gpu_autograd_baseline": gpu_cmp,
             "loss": loss, "wall_s_timed_region": t_wall,
             "step_ms_stats": {"min": float(step_ms.min()), "median": float(np.median(step_ms)),

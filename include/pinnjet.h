@@ -120,6 +120,19 @@ int pj_forward_train(const PjSpec* spec, const int32_t* prog_train /*device*/, i
                      float loss_scale, const float* rbar, float* resid_out, float* sumsq_out,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same two calls with the problem's SPECIALISED forward kernel: cu_function is the CUfunction handle
+ * of `pj_k1_jit` in a module the caller compiled from csrc/pinnjet_jit.cu with the problem's programs generated as
+ * straight-line CUDA (neurodiffeq_b200/jit.py) and loaded with cuModuleLoadData.  Same buffers, plan and results as
+ * pj_forward / pj_forward_train (the program arguments are still required: they size the plan); tensor-core path only,
+ * no external cotangents. */
+int pj_forward_jit(void* cu_function, const PjSpec* spec, const int32_t* prog_eval, int32_t prog_len, const int32_t* prog_w,
+                   int32_t prog_w_len, const float* const* coords, int64_t n_points, const float* theta_pack, float* u_out,
+                   float* resid_out, float* sumsq_out, void* workspace, size_t workspace_bytes, void* stream);
+int pj_forward_train_jit(void* cu_function, const PjSpec* spec, const int32_t* prog_train, int32_t prog_len,
+                         const int32_t* prog_w, int32_t prog_w_len, const float* const* coords, int64_t n_points,
+                         const float* theta_pack, float loss_scale, float* resid_out, float* sumsq_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* Reverse pass: grad_theta += dL/dtheta  (replaces loss.backward(), solvers.py:393).
  * Must follow pj_forward_train on the same workspace / points / theta_pack.                                    */
 int pj_backward(const PjSpec* spec, const float* const* coords, int64_t n_points, const float* theta_pack,

@@ -4,6 +4,7 @@
 #include <cstdarg>
 
 #include <cstdlib>
+#include <dlfcn.h>
 #include <cuda_bf16.h>
 
 #include "pinnjet_common.cuh"
@@ -27,6 +28,7 @@ PJ_DECL(2, 1, 2)   // combined second-order channel over 2 / 3 weighted directio
 PJ_DECL(3, 1, 3)
 PJ_DECL(4, 1, 4)   // 4 directions (e.g. x, t, a boundary abscissa and one polarisation direction), combined only
 #undef PJ_DECL
+cudaError_t launch_tc_relayout(const K1Args& a, cudaStream_t s);
 cudaError_t launch_reduce(const float* gpart, int n_parts, long long n_theta, float* grad, cudaStream_t s);
 cudaError_t launch_loss_finalize(const float* part, int n_parts, float* out, cudaStream_t s);
 
@@ -542,10 +544,22 @@ int pj_pack(const PjSpec* spec, const float* theta, float* theta_pack, void* str
     return check_cuda(cudaGetLastError(), "pack launch");
 }
 
+// The specialised forward kernel (neurodiffeq_b200/jit.py) arrives as a CUfunction handle of a module the caller loaded:
+// launched through the driver API, resolved lazily so that the library itself does not link against libcuda.
+typedef int (*CuLaunchKernel)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**, void**);
+static CuLaunchKernel cu_launch_kernel() {
+    static CuLaunchKernel fn = nullptr;
+    if (!fn) {
+        void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (h) fn = reinterpret_cast<CuLaunchKernel>(dlsym(h, "cuLaunchKernel"));
+    }
+    return fn;
+}
+
 static int run_k1(const PjSpec* spec, const int32_t* prog, int32_t prog_len, const int32_t* prog_w, int32_t prog_w_len,
                   const float* const* coords, int64_t n,
                   const float* theta_pack, int mode, float loss_scale, const float* rbar, float* u_out, float* r_out,
-                  float* sumsq_out, void* ws, size_t ws_bytes, void* stream) {
+                  float* sumsq_out, void* ws, size_t ws_bytes, void* stream, void* jit_function = nullptr) {
     if (!spec || !prog || !coords || !theta_pack || !ws) return fail(-1, "null argument");
     K1Args a;
     memset(&a, 0, sizeof(a));
@@ -579,7 +593,18 @@ static int run_k1(const PjSpec* spec, const int32_t* prog, int32_t prog_len, con
     a.seeds = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_seed) : nullptr;
     a.wts = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_wts) : nullptr;
     const SchemeEntry* e = find_scheme(spec->n1, spec->n2, spec->wl);
-    if (int rc = check_cuda((a.plan.tc ? e->k1tc : e->k1)(a, a.plan.grid, a.plan.k1_bytes, (cudaStream_t)stream), "forward launch")) return rc;
+    if (jit_function) {   // the problem's own forward kernel: same arguments, same plan; then the record copy of the isolation mode
+        if (!a.plan.tc) return fail(-2, "the specialised forward kernel exists for the tensor-core path only");
+        CuLaunchKernel launch = cu_launch_kernel();
+        if (!launch) return fail(-4, "libcuda.so.1 / cuLaunchKernel not available");
+        void* params[1] = {&a};
+        const int rc = launch(jit_function, (unsigned)a.plan.grid, 1, 1, 640, 1, 1, (unsigned)a.plan.k1_bytes, stream, params, nullptr);
+        if (rc != 0) return fail(-5, "cuLaunchKernel of the specialised forward kernel failed (%d)", rc);
+        if (mode == 1 && !a.plan.tc_bwd)
+            if (int rc2 = check_cuda(launch_tc_relayout(a, (cudaStream_t)stream), "record re-layout")) return rc2;
+    } else if (int rc = check_cuda((a.plan.tc ? e->k1tc : e->k1)(a, a.plan.grid, a.plan.k1_bytes, (cudaStream_t)stream), "forward launch")) {
+        return rc;
+    }
     if (sumsq_out)
         return check_cuda(launch_loss_finalize(a.loss_part, a.plan.tc ? 2 * a.plan.grid : a.plan.grid, sumsq_out, (cudaStream_t)stream),
                           "loss finalize");
@@ -599,6 +624,23 @@ int pj_forward_train(const PjSpec* spec, const int32_t* prog_train, int32_t prog
                      size_t workspace_bytes, void* stream) {
     return run_k1(spec, prog_train, prog_len, prog_w, prog_w_len, coords, n_points, theta_pack, 1, loss_scale, rbar, nullptr, resid_out,
                   sumsq_out, workspace, workspace_bytes, stream);
+}
+
+int pj_forward_jit(void* cu_function, const PjSpec* spec, const int32_t* prog_eval, int32_t prog_len, const int32_t* prog_w,
+                   int32_t prog_w_len, const float* const* coords, int64_t n_points, const float* theta_pack, float* u_out,
+                   float* resid_out, float* sumsq_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!cu_function) return fail(-1, "null kernel handle");
+    return run_k1(spec, prog_eval, prog_len, prog_w, prog_w_len, coords, n_points, theta_pack, 0, 0.0f, nullptr, u_out, resid_out, sumsq_out,
+                  workspace, workspace_bytes, stream, cu_function);
+}
+
+int pj_forward_train_jit(void* cu_function, const PjSpec* spec, const int32_t* prog_train, int32_t prog_len, const int32_t* prog_w,
+                         int32_t prog_w_len, const float* const* coords, int64_t n_points, const float* theta_pack,
+                         float loss_scale, float* resid_out, float* sumsq_out, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+    if (!cu_function) return fail(-1, "null kernel handle");
+    return run_k1(spec, prog_train, prog_len, prog_w, prog_w_len, coords, n_points, theta_pack, 1, loss_scale, nullptr, nullptr, resid_out,
+                  sumsq_out, workspace, workspace_bytes, stream, cu_function);
 }
 
 int pj_backward(const PjSpec* spec, const float* const* coords, int64_t n_points, const float* theta_pack,

@@ -49,6 +49,23 @@ __global__ void loss_finalize_kernel(const float* __restrict__ part, int n_parts
     if (threadIdx.x == 0) out[0] += s;
 }
 
+// record copy of the isolation mode (PINNJET_TC=1), also used behind the specialised forward kernel
+cudaError_t launch_tc_relayout(const K1Args& a, cudaStream_t s) {
+    int n_hidden = 0;
+    for (int n = 0; n < a.spec.n_nets; ++n) n_hidden += a.spec.net[n].n_linear - 1;
+    const unsigned grid = (unsigned)(a.plan.n_tiles1 * n_hidden);
+    switch (a.plan.C) {
+        case 2: tc_relayout_records_kernel<2><<<grid, TC_NT, 0, s>>>(a, a.zj, a.zj_ffma); break;
+        case 3: tc_relayout_records_kernel<3><<<grid, TC_NT, 0, s>>>(a, a.zj, a.zj_ffma); break;
+        case 4: tc_relayout_records_kernel<4><<<grid, TC_NT, 0, s>>>(a, a.zj, a.zj_ffma); break;
+        case 5: tc_relayout_records_kernel<5><<<grid, TC_NT, 0, s>>>(a, a.zj, a.zj_ffma); break;
+        case 6: tc_relayout_records_kernel<6><<<grid, TC_NT, 0, s>>>(a, a.zj, a.zj_ffma); break;
+        case 7: tc_relayout_records_kernel<7><<<grid, TC_NT, 0, s>>>(a, a.zj, a.zj_ffma); break;
+        default: return cudaErrorNotSupported;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_reduce(const float* gpart, int n_parts, long long n_theta, float* grad, cudaStream_t s) {
     k2_reduce_kernel<<<(unsigned)((n_theta + 63) / 64), 256, 0, s>>>(gpart, n_parts, n_theta, grad);
     return cudaGetLastError();

@@ -29,8 +29,18 @@ constexpr int K1T_THREADS = TC_NT + 32 + 32 * K1T_NPW + 32;  // 640
 constexpr int K1T_EB = 32 * K1T_NPW;                         // points per program batch (a whole number of tiles)
 constexpr int K1T_RING = 4;                                  // tile buffers of the prefetch warp
 
-template <int N1, int N2, int WL>
-__global__ void __launch_bounds__(K1T_THREADS, 1) k1tc3_forward_kernel(const __grid_constant__ K1Args A) {
+// JIT = true (csrc/pinnjet_jit.cu, neurodiffeq_b200/jit.py): the three programs of the problem are compiled into the kernel
+// as straight-line code (pj_jit_program_train / _eval / _w) instead of being interpreted.
+#ifndef PJ_JIT
+namespace {
+__device__ __forceinline__ float pj_jit_program_train(const ProgIO&) { return 0.0f; }
+__device__ __forceinline__ float pj_jit_program_eval(const ProgIO&) { return 0.0f; }
+__device__ __forceinline__ float pj_jit_program_w(const ProgIO&) { return 0.0f; }
+}  // namespace
+#endif
+
+template <int N1, int N2, int WL, bool JIT>
+__device__ __forceinline__ void k1tc3_body(const K1Args& A) {
     constexpr int C = 1 + N1 + N2;
     using G = TcGeo<C>;
     constexpr int UG = G::UG, TP = G::TP;
@@ -181,8 +191,15 @@ __global__ void __launch_bounds__(K1T_THREADS, 1) k1tc3_forward_kernel(const __g
             }
             if constexpr (WL > 0) {   // per-point weights of the combined second-order channel (coordinate-only expressions)
                 for (int pt = lane; pt < TP; pt += 32) {
-                    run_program_rt(progw_s, A.prog_w_len, wslots + lane, A.coords, min(base + pt, A.N - 1), A.N, nullptr, 0,
-                                   nullptr, 0.0f, nullptr, nullptr, nullptr, TP, wb + pt, TP);
+                    if constexpr (JIT) {
+                        ProgIO io{A.coords, min(base + pt, A.N - 1), A.N, nullptr, 0, nullptr, 0.0f, nullptr, nullptr, nullptr, TP};
+                        io.w_out = wb + pt;
+                        io.w_stride = TP;
+                        pj_jit_program_w(io);
+                    } else {
+                        run_program_rt(progw_s, A.prog_w_len, wslots + lane, A.coords, min(base + pt, A.N - 1), A.N, nullptr, 0,
+                                       nullptr, 0.0f, nullptr, nullptr, nullptr, TP, wb + pt, TP);
+                    }
                 }
                 __syncwarp();
                 if (train)   // K2 needs the same weights: workspace [tile of sT points][NW][sT]
@@ -222,8 +239,13 @@ __global__ void __launch_bounds__(K1T_THREADS, 1) k1tc3_forward_kernel(const __g
                 float* seed_tile = (train && gidx < ws_points)
                                        ? A.seeds + (gidx / sT) * ((long long)sp.n_yrows * sT) + (gidx % sT) : nullptr;
                 if (gidx < A.N) {
-                    my_sumsq += run_program_rt(prog_s, A.prog_len, my_slots, A.coords, gidx, A.N, yb + bp, K1T_EB, A.rbar,
-                                               A.loss_scale, A.u_out, A.r_out, seed_tile, sT, nullptr, 0);
+                    if constexpr (JIT) {
+                        ProgIO io{A.coords, gidx, A.N, yb + bp, K1T_EB, A.rbar, A.loss_scale, A.u_out, A.r_out, seed_tile, sT};
+                        my_sumsq += train ? pj_jit_program_train(io) : pj_jit_program_eval(io);
+                    } else {
+                        my_sumsq += run_program_rt(prog_s, A.prog_len, my_slots, A.coords, gidx, A.N, yb + bp, K1T_EB, A.rbar,
+                                                   A.loss_scale, A.u_out, A.r_out, seed_tile, sT, nullptr, 0);
+                    }
                 } else if (seed_tile) {
                     for (int r = 0; r < sp.n_yrows; ++r) seed_tile[r * sT] = 0.0f;   // padded points: zero adjoint
                 }
@@ -375,6 +397,11 @@ __global__ void __launch_bounds__(K1T_THREADS, 1) k1tc3_forward_kernel(const __g
     tc_fence_before();
     bar_named(9, TC_NT);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
+}
+
+template <int N1, int N2, int WL>
+__global__ void __launch_bounds__(K1T_THREADS, 1) k1tc3_forward_kernel(const __grid_constant__ K1Args A) {
+    k1tc3_body<N1, N2, WL, false>(A);
 }
 
 // Bring-up / isolation helper (PINNJET_TC=1): copies the tensor-core records [tile][layer][thread][C*UG] into the layout

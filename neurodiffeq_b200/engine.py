@@ -75,7 +75,11 @@ def load_library():
     lib.pj_forward_train.argtypes = [ctypes.POINTER(PjSpec), vp, i32, vp, i32, ctypes.POINTER(vp), i64, vp, f32, vp, vp,
                                      vp, vp, ctypes.c_size_t, vp]
     lib.pj_backward.argtypes = [ctypes.POINTER(PjSpec), ctypes.POINTER(vp), i64, vp, vp, vp, ctypes.c_size_t, vp]
-    for fn in (lib.pj_sizes, lib.pj_pack, lib.pj_forward, lib.pj_forward_train, lib.pj_backward):
+    lib.pj_forward_jit.argtypes = [vp] + list(lib.pj_forward.argtypes)
+    lib.pj_forward_train_jit.argtypes = [vp, ctypes.POINTER(PjSpec), vp, i32, vp, i32, ctypes.POINTER(vp), i64, vp, f32, vp, vp,
+                                         vp, ctypes.c_size_t, vp]
+    for fn in (lib.pj_sizes, lib.pj_pack, lib.pj_forward, lib.pj_forward_train, lib.pj_backward, lib.pj_forward_jit,
+               lib.pj_forward_train_jit):
         fn.restype = ctypes.c_int
     if lib.pj_abi_version() != 2:
         raise RuntimeError("libpinnjet.so ABI version mismatch")
@@ -84,7 +88,8 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ("pj_abi_version", "pj_last_error", "pj_sizes", "pj_plan_info", "pj_pack", "pj_forward", "pj_forward_train",
-                    "pj_backward", "pj_allreduce_bytes", "pj_allreduce_oneshot", "pj_sample", "pj_adam_step")
+                    "pj_backward", "pj_allreduce_bytes", "pj_allreduce_oneshot", "pj_sample", "pj_adam_step", "pj_forward_jit",
+                    "pj_forward_train_jit")
 
 
 def _check(rc, what):
@@ -169,6 +174,9 @@ class FusedProblem:
         self._ws_points = 0
         self.kernel_launches = 0
         self._graphs = {}
+        self._jit, self._jit_ok, self.jit_reason = None, {}, "not requested"
+        if os.environ.get("PINNJET_JIT") == "1":
+            self.enable_jit()
 
     # ---- parameters: one flat fp32 buffer, nn.Parameters become views (torch layout preserved) ----------------------
     def _adopt_parameters(self):
@@ -397,12 +405,13 @@ class FusedProblem:
         r = torch.empty((self.n_eq, n), dtype=torch.float32, device=self.device) if want_residual else None
         if want_sumsq:
             self.sumsq.zero_()
-        _check(self.lib.pj_forward(ctypes.byref(self.spec), self.prog_eval.data_ptr(), len(self.tp.prog_eval),
-                                   *self._prog_w_args(), ptrs, n,
-                                   self.pack_buf.data_ptr(), u.data_ptr() if want_u else None,
-                                   r.data_ptr() if want_residual else None,
-                                   self.sumsq.data_ptr() if want_sumsq else None,
-                                   self.workspace.data_ptr(), self.workspace.numel(), self._stream()), "pj_forward")
+        args = (ctypes.byref(self.spec), self.prog_eval.data_ptr(), len(self.tp.prog_eval), *self._prog_w_args(), ptrs, n,
+                self.pack_buf.data_ptr(), u.data_ptr() if want_u else None, r.data_ptr() if want_residual else None,
+                self.sumsq.data_ptr() if want_sumsq else None, self.workspace.data_ptr(), self.workspace.numel(), self._stream())
+        if self._jit_usable(n):
+            _check(self.lib.pj_forward_jit(self._jit.function, *args), "pj_forward_jit")
+        else:
+            _check(self.lib.pj_forward(*args), "pj_forward")
         self.kernel_launches += 2 if want_sumsq else 1
         return u, r, (self.sumsq if want_sumsq else None)
 
@@ -437,18 +446,56 @@ class FusedProblem:
                 raise ValueError(f"ubar must have shape ({self.n_funcs}, {n})")
             prog, prog_len = self.enable_function_adjoints(), len(self.tp.prog_train_ext_u)
             rbar = torch.cat([rbar, ubar], dim=0).contiguous()
-        _check(self.lib.pj_forward_train(ctypes.byref(self.spec), prog.data_ptr(), prog_len, *self._prog_w_args(), ptrs, n,
-                                         self.pack_buf.data_ptr(), ctypes.c_float(scale),
-                                         rbar.data_ptr() if rbar is not None else None,
-                                         r.data_ptr() if want_residual else None, sumsq_out.data_ptr(),
-                                         self.workspace.data_ptr(), self.workspace.numel(), self._stream()),
-               "pj_forward_train")
+        if rbar is None and self._jit_usable(n):   # the problem's own forward kernel (programs compiled in): jit.py
+            _check(self.lib.pj_forward_train_jit(self._jit.function, ctypes.byref(self.spec), prog.data_ptr(), prog_len,
+                                                 *self._prog_w_args(), ptrs, n, self.pack_buf.data_ptr(), ctypes.c_float(scale),
+                                                 r.data_ptr() if want_residual else None, sumsq_out.data_ptr(),
+                                                 self.workspace.data_ptr(), self.workspace.numel(), self._stream()),
+                   "pj_forward_train_jit")
+        else:
+            _check(self.lib.pj_forward_train(ctypes.byref(self.spec), prog.data_ptr(), prog_len, *self._prog_w_args(), ptrs, n,
+                                             self.pack_buf.data_ptr(), ctypes.c_float(scale),
+                                             rbar.data_ptr() if rbar is not None else None,
+                                             r.data_ptr() if want_residual else None, sumsq_out.data_ptr(),
+                                             self.workspace.data_ptr(), self.workspace.numel(), self._stream()),
+                   "pj_forward_train")
         if self._skips:
             self._accumulate_shortcut_grads(keep, n)
         _check(self.lib.pj_backward(ctypes.byref(self.spec), ptrs, n, self.pack_buf.data_ptr(), self.grad.data_ptr(),
                                     self.workspace.data_ptr(), self.workspace.numel(), self._stream()), "pj_backward")
         self.kernel_launches += 4
         return sumsq_out, r
+
+    # ---- specialised forward kernel (jit.py): the programs compiled into the kernel instead of interpreted ---------------
+    def enable_jit(self, strict=False):
+        """Compile (or fetch from the disk cache) and load this problem's specialised forward kernel.  Returns True when it
+        is in use afterwards; problems it does not cover keep the interpreter (``self.jit_reason`` says why; ``strict=True``
+        raises instead).  Results are identical to the interpreter's: same operations, same rounding."""
+        if self._jit is not None:
+            return True
+        try:
+            if self._patch_sets:
+                raise ValueError("the program has trainable immediates (Resnet shortcut)")
+            if not self.plan_info(1024)["tc"]:
+                raise ValueError("the network is not on the tensor-core path (hidden width != 64 or PINNJET_TC=0)")
+            from .jit import JitKernel
+            self._jit = JitKernel(self.tp, self.device)
+            self._graphs.clear()                 # captured graphs hold the interpreter kernel
+            self.jit_reason = ""
+            return True
+        except Exception as exc:  # noqa: BLE001
+            if strict:
+                raise
+            self.jit_reason = f"{type(exc).__name__}: {exc}"
+            return False
+
+    def _jit_usable(self, n_points):
+        if self._jit is None:
+            return False
+        ok = self._jit_ok.get(n_points)
+        if ok is None:                           # the plan may leave the tensor-core path for a given size / environment
+            ok = self._jit_ok[n_points] = bool(self.plan_info(n_points)["tc"])
+        return ok
 
     def plan_info(self, n_points):
         """Tiling plan (diagnostics): dict with T, RS, grid, ... plus padded widths and z-jet offsets per net."""

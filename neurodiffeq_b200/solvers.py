@@ -13,6 +13,7 @@ K0 pack -> K1 -> K2 (-> NCCL all-reduce when ``torch.distributed`` is initialise
 back ONCE per epoch instead of ``.item()`` per batch (:394); the best parameters are kept as a flat device copy
 instead of ``deepcopy(nets)`` per improvement (:441).  Unsupported features raise instead of silently falling back.
 """
+import os
 import sys
 import types
 import warnings
@@ -111,7 +112,7 @@ class BaseSolver:
     def __init__(self, diff_eqs, conditions, nets=None, train_generator=None, valid_generator=None,
                  analytic_solutions=None, optimizer=None, loss_fn=None, n_batches_train=1, n_batches_valid=4,
                  metrics=None, n_input_units=None, n_output_units=None, shuffle=None, batch_size=None,
-                 device=None, data_parallel=True, device_loop=False):
+                 device=None, data_parallel=True, device_loop=False, jit=False):
         if shuffle:
             warnings.warn("param `shuffle` is deprecated and ignored; shuffling should be performed by generators",
                           FutureWarning)
@@ -168,6 +169,8 @@ class BaseSolver:
                                         enforce=self.compute_func_val)
             self.n_eq = self.problem.n_eq - (n_coords if self._h1 else 0)     # the user's equations
         self.device = self.problem.device
+        if jit or os.environ.get("PINNJET_JIT") == "1":   # opt-in: the residual programs compiled into the forward kernel
+            self.problem.enable_jit()
 
         self.optimizer = optimizer if optimizer else torch.optim.Adam(
             _unique(chain.from_iterable(n.parameters() for n in self.nets)))
