@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--fit-epochs", type=int, default=200, help="epochs of the Solver.fit leg (0 = skip)")
     ap.add_argument("--no-gpu-comparator", action="store_true", help="skip the torch-CUDA-autograd comparator leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-strong", action="store_true", help="skip the C3 / C5 strong-scaling legs")
     return ap.parse_args()
 
 
@@ -139,7 +140,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = workloads.build(__import__("helpers").product_namespace(), args.workload)
+    wl = workloads.build(workloads.product_namespace(), args.workload)
     n = args.points or wl.default_n
     # The reference computes in torch's default dtype, float32 (it never calls set_default_dtype): that is the headline of
     # this arm.  float64 -- the precision of the parity oracle -- is timed beside it (BASELINE.md §3 asks for both).
@@ -243,7 +244,7 @@ def fit_throughput(key, n, epochs, warm=20, device_loop=False):
     ``device_loop=True`` (opt-in of the solvers): Philox sampling on the device, K0..K2b, best-parameter bookkeeping and
     Adam (optim.FlatAdam) replayed as ONE CUDA graph per epoch; the loss history is read back once at the end."""
     from neurodiffeq_b200 import solvers as S, generators as G
-    nd = __import__("helpers").product_namespace()
+    nd = workloads.product_namespace()
     wl = workloads.build(nd, key)
     torch.manual_seed(0)
     nets, conds = wl.make_nets(), wl.make_conditions()
@@ -271,6 +272,70 @@ def fit_throughput(key, n, epochs, warm=20, device_loop=False):
                      f"per epoch, n_batches_valid=0, wall clock")}
 
 
+def strong_scaling_leg(key, n_global, world, rank, dev, steps, warmup, flush_l2):
+    """BASELINE configs 3 and 5 (C3 Burgers 65536 points, C5 bundle 131072 points): the GLOBAL batch is fixed and sharded
+    over the ranks; step = pack + K1 + finalize + K2 + K2b + the collective, replayed as a CUDA graph, L2 flushed before each
+    timed step, max over ranks.  Reported as an extra key of the bench line (the headline stays C2 weak scaling)."""
+    import torch.distributed as dist
+    from neurodiffeq_b200.parallel import GradBufReducer, shard_bounds
+    wl, nets, conds, fp = workloads.build_fused(key, seed=0, device=dev)
+    lo, hi = shard_bounds(n_global, rank, world)
+    coords_np = workloads.sample_coords(wl, n_global, seed=2000)
+    coords = [torch.from_numpy(c[lo:hi].copy()).to(dev) for c in coords_np]
+    if os.environ.get("PINNJET_JIT", "1") != "0":
+        fp.enable_jit()
+    fp.gradbuf.zero_()
+    fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq)
+    reducer = GradBufReducer(fp.gradbuf, dist) if world > 1 else None
+
+    def body():
+        fp.gradbuf.zero_()
+        fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq)
+        if reducer is not None:
+            reducer(fp.gradbuf)
+
+    for _ in range(max(warmup, 3)):
+        body()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        body()
+    torch.cuda.current_stream().wait_stream(side)
+    if world > 1:
+        dist.barrier()
+    with torch.cuda.graph(graph):
+        body()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total = 0.0
+    for _ in range(steps):
+        flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        total += a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t.item())
+    ms = total / steps
+    info = fp.plan_info(hi - lo)
+    out = {"workload": wl.name, "global_points": n_global, "points_per_gpu": hi - lo, "ms_per_step": ms,
+           "points_per_s": n_global / (ms * 1e-3), "steps": steps, "loss": float(fp.sumsq.item()) / (n_global * fp.n_eq),
+           "kernels": ("tensor-core" if info.get("tc") else "ffma") + " / " + ("tensor-core" if info.get("tc_bwd") else "ffma"),
+           "collective": reducer.mode if reducer is not None else "single"}
+    del graph, fp
+    torch.cuda.empty_cache()
+    return out
+
+
 def executed_flops(wl, tp):
     """F = sum over nets of 2*d0*h1 + C*2*(sum h_{l-1} h_l + h_L*d_out) with the channel count the kernels really carry."""
     c_exec, total = tp.n_channels, 0
@@ -295,7 +360,7 @@ def main():
         return run_reference_arm(args)
 
     import ctypes
-    from helpers import build_fused
+    build_fused = workloads.build_fused
     from neurodiffeq_b200 import engine as E
 
     rank = int(os.environ.get("RANK", "0"))
@@ -549,6 +614,16 @@ def main():
         cpu_base = {**{k: cpu32[k] for k in ("value", "unit", "cores", "kind", "sample")},   # float32 = the reference's dtype
                     "f64": {k: cpu64[k] for k in ("value", "unit", "cores", "sample")}}
 
+    # ---- strong scaling of the two BASELINE configs that name it (C3: 65536 points, C5: 131072 points over the N GPUs) -----
+    strong = None
+    if args.workload == "c2" and not args.points and not args.no_strong:
+        strong = {}
+        for key, n_g in (("c3", 65536), ("c5", 131072)):
+            try:
+                strong[key] = strong_scaling_leg(key, n_g, world, rank, dev, steps=min(args.steps, 30), warmup=3, flush_l2=flush_l2)
+            except Exception as e:  # noqa: BLE001  (secondary report)
+                strong[key] = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
@@ -564,6 +639,7 @@ def main():
                     "d2h_bytes_per_step": 4},
             "gpu_launches": ours_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks, "collective": collective,
+            "strong_scaling": strong,
             "specialised_forward_kernel": {"in_use": bool(jit_on), "why_not": "" if jit_on else fp.jit_reason,
                                            "what": "residual programs compiled into k1tc3 (neurodiffeq_b200/jit.py, nvcc, "
                                                    "cached); PINNJET_JIT=0 keeps the in-kernel interpreter"},

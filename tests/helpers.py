@@ -7,50 +7,11 @@ import torch
 import workloads
 
 
-def product_namespace():
-    from neurodiffeq_b200 import diff
-    from neurodiffeq_b200 import operators as ops
-    from neurodiffeq_b200.networks import FCNN, SinActv, Resnet
-    from neurodiffeq_b200 import conditions as c
-    return types.SimpleNamespace(
-        diff=diff, FCNN=FCNN, Resnet=Resnet, SinActv=SinActv, IVP=c.IVP, BundleIVP=c.BundleIVP, DirichletBVP2D=c.DirichletBVP2D,
-        IBVP1D=c.IBVP1D, DirichletBVPSpherical=c.DirichletBVPSpherical, NoCondition=c.NoCondition,
-        DoubleEndedBVP1D=c.DoubleEndedBVP1D, EnsembleCondition=c.EnsembleCondition,
-        spherical_laplacian=ops.spherical_laplacian, laplacian=ops.laplacian, grad=ops.grad, div=ops.div,
-        curl=ops.curl)
-
-
-def distinct(nets):
-    seen, out = set(), []
-    for n in nets:
-        if id(n) not in seen:
-            seen.add(id(n))
-            out.append(n)
-    return out
-
-
-def set_params(nets, arrays):
-    it = iter(arrays)
-    with torch.no_grad():
-        for m in distinct(nets):
-            for p in m.parameters():
-                p.copy_(torch.as_tensor(next(it), dtype=p.dtype).reshape(p.shape))
+from workloads import product_namespace, build_fused, set_params, distinct  # noqa: E402,F401  (shared with bench.py / smoke())
 
 
 def get_params(nets):
     return [p.detach().cpu().numpy().copy() for m in distinct(nets) for p in m.parameters()]
-
-
-def build_fused(key, params=None, seed=0, device=None):
-    """The product: trace the workload with neurodiffeq_b200's own classes and put it on the GPU."""
-    from neurodiffeq_b200.engine import FusedProblem
-    wl = workloads.build(product_namespace(), key)
-    torch.manual_seed(seed)
-    nets, conds = wl.make_nets(), wl.make_conditions()
-    if params is not None:
-        set_params(nets, params)
-    fp = FusedProblem(nets, conds, workloads.bundle_eq_wrapper(wl), len(wl.coord_names), device=device)
-    return wl, nets, conds, fp
 
 
 def oracle_eval(key, params, coords, dtype=torch.float64, backward=True):

@@ -287,3 +287,49 @@ def operator_arguments(name, coords):
         return tuple(coords)
     f = operator_fields(*coords)
     return (f[0], *coords) if name in _SCALAR_OPERATORS else (*f, *coords)
+
+
+# ---- the product on a workload (shared by tests/, bench.py and __graft_entry__.smoke()) --------------------------------------
+def product_namespace():
+    import types
+    from neurodiffeq_b200 import diff
+    from neurodiffeq_b200 import operators as ops
+    from neurodiffeq_b200.networks import FCNN, SinActv, Resnet
+    from neurodiffeq_b200 import conditions as c
+    return types.SimpleNamespace(
+        diff=diff, FCNN=FCNN, Resnet=Resnet, SinActv=SinActv, IVP=c.IVP, BundleIVP=c.BundleIVP, DirichletBVP2D=c.DirichletBVP2D,
+        IBVP1D=c.IBVP1D, DirichletBVPSpherical=c.DirichletBVPSpherical, NoCondition=c.NoCondition,
+        DoubleEndedBVP1D=c.DoubleEndedBVP1D, EnsembleCondition=c.EnsembleCondition,
+        spherical_laplacian=ops.spherical_laplacian, laplacian=ops.laplacian, grad=ops.grad, div=ops.div,
+        curl=ops.curl)
+
+
+def distinct(nets):
+    seen, out = set(), []
+    for n in nets:
+        if id(n) not in seen:
+            seen.add(id(n))
+            out.append(n)
+    return out
+
+
+def set_params(nets, arrays):
+    import torch
+    it = iter(arrays)
+    with torch.no_grad():
+        for m in distinct(nets):
+            for p in m.parameters():
+                p.copy_(torch.as_tensor(next(it), dtype=p.dtype).reshape(p.shape))
+
+
+def build_fused(key, params=None, seed=0, device=None):
+    """The product: trace the workload with neurodiffeq_b200's own classes and put it on the GPU."""
+    import torch
+    from neurodiffeq_b200.engine import FusedProblem
+    wl = build(product_namespace(), key)
+    torch.manual_seed(seed)
+    nets, conds = wl.make_nets(), wl.make_conditions()
+    if params is not None:
+        set_params(nets, params)
+    fp = FusedProblem(nets, conds, bundle_eq_wrapper(wl), len(wl.coord_names), device=device)
+    return wl, nets, conds, fp
