@@ -472,10 +472,15 @@ def main():
     cs = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
     scale = ctypes.c_float(2.0 / (n_global * fp.n_eq))
 
-    def k1_only():
-        E._check(fp.lib.pj_forward_train(sp, fp.prog_train.data_ptr(), len(fp.tp.prog_train), *fp._prog_w_args(), ptrs, n,
-                                         fp.pack_buf.data_ptr(), scale, None, None, None, fp.workspace.data_ptr(),
-                                         fp.workspace.numel(), cs()), "k1")
+    def k1_only():   # the forward kernel the step launches: the problem's specialised kernel when it is in use
+        if jit_on and fp._jit_usable(n):
+            E._check(fp.lib.pj_forward_train_jit(fp._jit.function, sp, fp.prog_train.data_ptr(), len(fp.tp.prog_train),
+                                                 *fp._prog_w_args(), ptrs, n, fp.pack_buf.data_ptr(), scale, None, None,
+                                                 fp.workspace.data_ptr(), fp.workspace.numel(), cs()), "k1 (specialised)")
+        else:
+            E._check(fp.lib.pj_forward_train(sp, fp.prog_train.data_ptr(), len(fp.tp.prog_train), *fp._prog_w_args(), ptrs, n,
+                                             fp.pack_buf.data_ptr(), scale, None, None, None, fp.workspace.data_ptr(),
+                                             fp.workspace.numel(), cs()), "k1")
 
     def k2_only():
         E._check(fp.lib.pj_backward(sp, ptrs, n, fp.pack_buf.data_ptr(), fp.grad.data_ptr(), fp.workspace.data_ptr(),
@@ -571,7 +576,8 @@ def main():
         with open(tpath) as f:
             traffic = json.load(f).get(args.workload, {}).get(k1_name, {}).get("dram_bytes")
     roofline = {
-        "kernel": k1_name + " (forward + jets + residual program)",
+        "kernel": k1_name + (" specialised (pj_k1_jit: residual programs compiled in)" if jit_on else "") +
+                  " (forward + jets + residual program)",
         "bound": "tensor", "achieved": ach_k1,
         "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach_k1 / bf16_peak, "traffic": traffic,
         "peak_source": f"dense bf16 tensor, {peak_src}",
