@@ -272,7 +272,7 @@ def fit_throughput(key, n, epochs, warm=20, device_loop=False):
                      f"per epoch, n_batches_valid=0, wall clock")}
 
 
-def strong_scaling_leg(key, n_global, world, rank, dev, steps, warmup, flush_l2):
+def strong_scaling_leg(key, n_global, world, rank, dev, steps, warmup, flush_l2, align=None):
     """BASELINE configs 3 and 5 (C3 Burgers 65536 points, C5 bundle 131072 points): the GLOBAL batch is fixed and sharded
     over the ranks; step = pack + K1 + finalize + K2 + K2b + the collective, replayed as a CUDA graph, L2 flushed before each
     timed step, max over ranks.  Reported as an extra key of the bench line (the headline stays C2 weak scaling)."""
@@ -290,9 +290,7 @@ def strong_scaling_leg(key, n_global, world, rank, dev, steps, warmup, flush_l2)
 
     def body():
         fp.gradbuf.zero_()
-        fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq)
-        if reducer is not None:
-            reducer(fp.gradbuf)
+        fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq, reducer=reducer)
 
     for _ in range(max(warmup, 3)):
         body()
@@ -315,6 +313,8 @@ def strong_scaling_leg(key, n_global, world, rank, dev, steps, warmup, flush_l2)
     total = 0.0
     for _ in range(steps):
         flush_l2()
+        if align is not None:
+            align()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         graph.replay()
@@ -330,7 +330,8 @@ def strong_scaling_leg(key, n_global, world, rank, dev, steps, warmup, flush_l2)
     out = {"workload": wl.name, "global_points": n_global, "points_per_gpu": hi - lo, "ms_per_step": ms,
            "points_per_s": n_global / (ms * 1e-3), "steps": steps, "loss": float(fp.sumsq.item()) / (n_global * fp.n_eq),
            "kernels": ("tensor-core" if info.get("tc") else "ffma") + " / " + ("tensor-core" if info.get("tc_bwd") else "ffma"),
-           "collective": reducer.mode if reducer is not None else "single"}
+           "collective": (reducer.mode + (" (fused with K2b)" if reducer.fused_args is not None else ""))
+           if reducer is not None else "single"}
     del graph, fp
     torch.cuda.empty_cache()
     return out
@@ -392,19 +393,26 @@ def main():
     stream = torch.cuda.current_stream()
 
     jit_on = fp.enable_jit() if os.environ.get("PINNJET_JIT", "1") != "0" else False   # specialised forward kernel (jit.py)
-    reducer = None
+    reducer, align = None, None
 
     def step_body():
         fp.gradbuf.zero_()                                # optimizer.zero_grad() + loss accumulator
-        fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq)
-        if world > 1:
-            reducer(fp.gradbuf)                           # SUM of [grad | sum r^2] over the ranks (parallel.GradBufReducer)
+        # N > 1: SUM of [grad | sum r^2] over the ranks (parallel.GradBufReducer) -- K2b and the one-shot NVLink collective
+        # as ONE kernel (pj_backward_allreduce) when peer memory is available, K2b + the process group's all-reduce otherwise
+        fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq, reducer=reducer)
 
     if world > 1:
         from neurodiffeq_b200.parallel import GradBufReducer
         fp.gradbuf.zero_()
         fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq)   # allocates the buffers
         reducer = GradBufReducer(fp.gradbuf, dist)
+        # the ranks flush their L2 independently before every timed step; a device-side barrier (the one-shot kernel on a dummy
+        # buffer) after the flush lines the start events up, so that the flush's jitter is not charged to the step
+        align_buf = torch.zeros(8, dtype=torch.float32, device=dev)
+        aligner = GradBufReducer(align_buf, dist)
+        if aligner.mode == "oneshot-nvlink" and os.environ.get("PINNJET_BENCH_ALIGN", "1") != "0":
+            align = lambda: aligner(align_buf)            # noqa: E731
+    fused_collective = reducer is not None and reducer.fused_args is not None
 
     # warm-up (also sizes buffers, sets kernel attributes)
     for _ in range(max(args.warmup, 3)):
@@ -438,7 +446,7 @@ def main():
             step_body()
 
     launches_per_step = 1 + 5   # gradbuf fill (torch) is not ours; pack, K1, loss-finalize, K2, K2b are
-    ours_per_step = 5 + (1 if (reducer is not None and reducer.mode == "oneshot-nvlink") else 0)
+    ours_per_step = 5 + (1 if (reducer is not None and reducer.mode == "oneshot-nvlink" and not fused_collective) else 0)
 
     # ---- timed region: K steps, L2 flushed before each, CUDA events per step, max over ranks -------------------------
     if world > 1:
@@ -449,6 +457,8 @@ def main():
         t_wall0 = time.perf_counter()
         for a, b in ev:
             flush_l2()
+            if align is not None:
+                align()
             a.record()
             run_step()
             b.record()
@@ -523,9 +533,15 @@ def main():
         collective = {"mode": reducer.mode, "fallback_reason": reducer.why, "bytes": int(scratch.numel() * 4),
                       "ms_back_to_back": time_collective(lambda: reducer(fp.gradbuf)),
                       "nccl_all_reduce_ms_back_to_back": time_collective(lambda: dist.all_reduce(scratch)),
-                      "kernel": "pj::allreduce_oneshot_kernel (csrc/pinnjet_comm.cu): peer loads over NVLink, flags with "
-                                "st.release.sys / ld.acquire.sys, sum in rank order" if reducer.mode == "oneshot-nvlink" else
-                                "torch.distributed.all_reduce"}
+                      "fused_with_k2b": fused_collective,
+                      "kernel": ("pj::reduce_allreduce_kernel (csrc/pinnjet_comm.cu, pj_backward_allreduce): the reverse kernel's "
+                                 "per-CTA partials folded, published in the symmetric buffer and summed over the ranks in ONE "
+                                 "launch; " if fused_collective else "") +
+                                ("pj::allreduce_oneshot_kernel (stand-alone form, timed here back to back): peer loads over "
+                                 "NVLink, flags with st.release.sys / ld.acquire.sys, sum in rank order"
+                                 if reducer.mode == "oneshot-nvlink" else "torch.distributed.all_reduce"),
+                      "rank_alignment": "device-side barrier after each L2 flush, before the start event" if align is not None
+                                        else "none"}
 
     # ---- e2e: host coordinates in, loss out, through the public call -------------------------------------------------
     def e2e_step():
@@ -626,7 +642,8 @@ def main():
         strong = {}
         for key, n_g in (("c3", 65536), ("c5", 131072)):
             try:
-                strong[key] = strong_scaling_leg(key, n_g, world, rank, dev, steps=min(args.steps, 30), warmup=3, flush_l2=flush_l2)
+                strong[key] = strong_scaling_leg(key, n_g, world, rank, dev, steps=min(args.steps, 30), warmup=3, flush_l2=flush_l2,
+                                                 align=align)
             except Exception as e:  # noqa: BLE001  (secondary report)
                 strong[key] = {"error": f"{type(e).__name__}: {e}"}
 
@@ -637,7 +654,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl.name}: {wl.solver}, nets {wl.nets_spec}, {n} points/GPU, "
                                    f"residual+grad step = pack+K1+finalize+K2+K2b"
-                                   + (f" + all-reduce of [grad|loss] ({reducer.mode})" if world > 1 else ""),
+                                   + (f" + all-reduce of [grad|loss] ({reducer.mode}"
+                                      f"{', fused with K2b' if fused_collective else ''})" if world > 1 else ""),
                        "points_per_gpu": n, "global_points": n_global, "tile_points": info["T"],
                        "grid": info["grid"], "l2": "flushed before every timed step (256 MiB memset, then 256 MiB streamed read so the lines left are clean)",
                        "cuda_graph": graph is not None, "parallelism": f"dp{world} (points sharded)"},

@@ -153,6 +153,22 @@ int64_t pj_allreduce_bytes(int64_t n_floats);
 int pj_allreduce_oneshot(const uint64_t* peer_buffers /*host array [world]*/, int32_t rank, int32_t world,
                          const float* in /*device*/, float* out /*device*/, int64_t n_floats, void* stream);
 
+/* Reverse pass + collective as ONE step of the data-parallel path: K2, then a single kernel that folds the per-CTA gradient
+ * partials (what pj_backward's reduction does), adds them to gradbuf = [grad_theta | tail] (tail: n_tail floats the caller
+ * wants summed along, e.g. sum r^2) and PUSHES every value as one 64-bit word {epoch, value} into the symmetric buffer of
+ * every peer; each rank then polls its own buffer and sums the ranks' values in rank order:
+ *     gradbuf <- sum over ranks of (gradbuf + dL/dtheta of this rank's points),  bit-identical on every rank.
+ * No flag, fence or barrier between the ranks: the critical path is ONE one-way NVLink store (the stand-alone kernel needs
+ * a flag one way and the data back).  Same symmetric-buffer rules as pj_allreduce_oneshot, but its OWN buffer of
+ * pj_backward_allreduce_bytes(n_theta + n_tail, world) bytes, zero-initialised. */
+#define PJ_ARF_BLOCKS 160
+#define PJ_ARF_HEADER_BYTES 8192   /* one epoch counter per block; the {epoch, value} slots start here */
+int64_t pj_backward_allreduce_bytes(int64_t n_floats, int32_t world);
+int pj_backward_allreduce(const PjSpec* spec, const float* const* coords, int64_t n_points, const float* theta_pack,
+                          float* gradbuf /*device, [n_theta + n_tail]*/, int64_t n_tail, void* workspace,
+                          size_t workspace_bytes, const uint64_t* peer_buffers /*host array [world]*/, int32_t rank,
+                          int32_t world, void* stream);
+
 /* ---- collocation point sampling on the device (opt-in, the host generators stay the default) -----------
  * Replaces generator.get_examples() (generators.py:107-191 Generator1D, :194-314 Generator2D/3D, :572-655
  * GeneratorSpherical) + the host->device copy of the batch (solvers.py:340-345).  One law per coordinate (three

@@ -31,6 +31,8 @@ PJ_DECL(4, 1, 4)   // 4 directions (e.g. x, t, a boundary abscissa and one polar
 cudaError_t launch_tc_relayout(const K1Args& a, cudaStream_t s);
 cudaError_t launch_reduce(const float* gpart, int n_parts, long long n_theta, float* grad, cudaStream_t s);
 cudaError_t launch_loss_finalize(const float* part, int n_parts, float* out, cudaStream_t s);
+cudaError_t launch_reduce_allreduce(const unsigned long long* peers, int rank, int world, const float* gpart, int n_parts,
+                                    long long n_theta, float* buf, long long n, cudaStream_t s);   // pinnjet_comm.cu
 
 typedef cudaError_t (*K1Launch)(const K1Args&, int, int, cudaStream_t);
 typedef cudaError_t (*K2Launch)(const K2Args&, int, int, cudaStream_t);
@@ -643,9 +645,10 @@ int pj_forward_train_jit(void* cu_function, const PjSpec* spec, const int32_t* p
                   sumsq_out, workspace, workspace_bytes, stream, cu_function);
 }
 
-int pj_backward(const PjSpec* spec, const float* const* coords, int64_t n_points, const float* theta_pack,
-                float* grad_theta, void* workspace, size_t workspace_bytes, void* stream) {
-    if (!spec || !coords || !theta_pack || !grad_theta || !workspace) return fail(-1, "null argument");
+// K2 on the records / seeds pj_forward_train left in the workspace; the per-CTA gradient partials stay in the workspace
+static int run_k2(const PjSpec* spec, const float* const* coords, int64_t n_points, const float* theta_pack, void* workspace,
+                  size_t workspace_bytes, void* stream, const float** gpart, int* n_parts) {
+    if (!spec || !coords || !theta_pack || !workspace) return fail(-1, "null argument");
     K2Args a;
     memset(&a, 0, sizeof(a));
     a.spec = *spec;
@@ -664,7 +667,32 @@ int pj_backward(const PjSpec* spec, const float* const* coords, int64_t n_points
     a.dbg = reinterpret_cast<float*>(w + a.plan.ws_loss) + 640;
     const SchemeEntry* e = find_scheme(spec->n1, spec->n2, spec->wl);
     if (int rc = check_cuda(e->k2(a, a.plan.grid_bwd, a.plan.k2_bytes, (cudaStream_t)stream), "backward launch")) return rc;
-    return check_cuda(launch_reduce(a.gpart, a.plan.grid_bwd, spec->n_theta, grad_theta, (cudaStream_t)stream), "reduce launch");
+    *gpart = a.gpart;
+    *n_parts = a.plan.grid_bwd;
+    return 0;
+}
+
+int pj_backward(const PjSpec* spec, const float* const* coords, int64_t n_points, const float* theta_pack,
+                float* grad_theta, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!grad_theta) return fail(-1, "null argument");
+    const float* gpart = nullptr;
+    int n_parts = 0;
+    if (int rc = run_k2(spec, coords, n_points, theta_pack, workspace, workspace_bytes, stream, &gpart, &n_parts)) return rc;
+    return check_cuda(launch_reduce(gpart, n_parts, spec->n_theta, grad_theta, (cudaStream_t)stream), "reduce launch");
+}
+
+int pj_backward_allreduce(const PjSpec* spec, const float* const* coords, int64_t n_points, const float* theta_pack,
+                          float* gradbuf, int64_t n_tail, void* workspace, size_t workspace_bytes,
+                          const uint64_t* peer_buffers, int32_t rank, int32_t world, void* stream) {
+    if (!gradbuf || !peer_buffers) return fail(-1, "null argument");
+    if (world < 1 || world > PJ_AR_MAX_RANKS || rank < 0 || rank >= world || n_tail < 0)
+        return fail(-1, "rank %d / world %d / n_tail %lld out of range", rank, world, (long long)n_tail);
+    const float* gpart = nullptr;
+    int n_parts = 0;
+    if (int rc = run_k2(spec, coords, n_points, theta_pack, workspace, workspace_bytes, stream, &gpart, &n_parts)) return rc;
+    return check_cuda(launch_reduce_allreduce(reinterpret_cast<const unsigned long long*>(peer_buffers), rank, world, gpart, n_parts,
+                                              spec->n_theta, gradbuf, spec->n_theta + n_tail, (cudaStream_t)stream),
+                      "reduce + all-reduce launch");
 }
 
 }  // extern "C"

@@ -22,6 +22,7 @@ namespace pj {
 
 struct ArArgs {
     unsigned long long buf[PJ_AR_MAX_RANKS];
+    unsigned long long self;   // buf[rank]
     int rank, world;
     long long n, n_pad;
 };
@@ -90,9 +91,122 @@ __global__ void __launch_bounds__(256) allreduce_oneshot_kernel(const ArArgs a, 
     if (tid == 0) *my_epoch = e;
 }
 
+// K2b and the collective in one kernel (pj_backward_allreduce), low-latency form: the stand-alone kernel above costs two
+// NVLink traversals plus two system-scope fences per call (flag over, data back: ~12 us measured at 2 GPUs, whether or not
+// K2b is merged in front of it), so this one PUSHES instead.  Every float travels as ONE 64-bit word {epoch, value}
+// (a scalar 8-byte store is single-copy atomic, also over NVLink): the receiver polls the word itself, so there is no flag,
+// no fence and no barrier between the ranks -- the critical path is one one-way store.
+//   symmetric buffer:  [epochs: PJ_ARF_BLOCKS x u32 | pad to PJ_ARF_HEADER_BYTES][slot 2][src rank world][n_pad] x u64
+//   chunk = 64 consecutive floats of [grad | tail]; CTA b owns chunks b, b + grid, ...; epoch e = CTA's counter + 1.
+//   phase 1 (per chunk): fold the per-CTA gradient partials in the fixed order of k2_reduce_kernel (4 groups of partials x
+//     64 parameters), add what the buffer already holds -> v; store {e, v} into slot[e & 1][my rank][i] of EVERY peer.
+//   phase 2 (per chunk): poll slot[e & 1][p][i] of the LOCAL buffer until its epoch is e, for every peer p (all loads in
+//     flight, re-polling only what is missing); sum in rank order (own value from the register) -> bit-identical on every
+//     rank and equal to K2b followed by the stand-alone kernel.
+// Slot reuse: a peer writes epoch e + 2 into the slot of e only after it finished e + 1, which needed this rank's e + 1
+// words, which this rank sends after its epoch-e kernel has completed (stream order).
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) reduce_allreduce_kernel(const ArArgs a, const float* __restrict__ gpart, int n_parts,
+                                                               long long n_theta, float* buf) {
+    __shared__ float red[4][64];
+    const int b = blockIdx.x, tid = threadIdx.x, il = tid & 63, g = tid >> 6;
+    unsigned char* me = reinterpret_cast<unsigned char*>(a.self);   // = a.buf[a.rank], without a dynamically indexed parameter
+    unsigned* my_epoch = reinterpret_cast<unsigned*>(me) + b;
+    const unsigned e = *my_epoch + 1u;
+    const long long slot_words = (long long)a.world * a.n_pad;                                  // u64 words per slot
+    const long long slot_off = PJ_ARF_HEADER_BYTES / 8 + (long long)(e & 1u) * slot_words;      // u64 words from the buffer start
+    const long long n_chunks = (a.n + 63) / 64;
+    const int per = (n_parts + 3) / 4, p_lo = g * per, p_hi = min(n_parts, p_lo + per);
+    float own = 0.0f;                       // the value of the CTA's first chunk stays in a register between the phases
+    int k = 0;
+    for (long long c = b; c < n_chunks; c += gridDim.x, ++k) {
+        const long long i = c * 64 + il;
+        float s = 0.0f;
+        if (i < n_theta) {
+            float s0 = 0.0f, s1 = 0.0f;
+            int p = p_lo;
+            for (; p + 1 < p_hi; p += 2) {
+                s0 += gpart[(size_t)p * n_theta + i];
+                s1 += gpart[(size_t)(p + 1) * n_theta + i];
+            }
+            if (p < p_hi) s0 += gpart[(size_t)p * n_theta + i];
+            s = s0 + s1;
+        }
+        red[g][il] = s;
+        __syncthreads();
+        if (g == 0 && i < a.n) {
+            const float v = buf[i] + ((red[0][il] + red[1][il]) + (red[2][il] + red[3][il]));
+            const unsigned long long word = ((unsigned long long)e << 32) | (unsigned long long)__float_as_uint(v);
+#pragma unroll
+            for (int p = 0; p < PJ_AR_MAX_RANKS; ++p)
+                if (p < a.world && p != a.rank)
+                    st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(a.buf[p]) + slot_off + (long long)a.rank * a.n_pad + i, word);
+            if (k == 0) own = v;
+            else st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(me) + slot_off + (long long)a.rank * a.n_pad + i, word);
+        }
+        __syncthreads();
+    }
+    if (g == 0) {
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(me) + slot_off;
+        k = 0;
+        for (long long c = b; c < n_chunks; c += gridDim.x, ++k) {
+            const long long i = c * 64 + il;
+            if (i >= a.n) continue;
+            unsigned long long w[PJ_AR_MAX_RANKS];
+            unsigned missing = 0;
+#pragma unroll
+            for (int p = 0; p < PJ_AR_MAX_RANKS; ++p)
+                if (p < a.world && !(p == a.rank && k == 0)) missing |= 1u << p;
+            while (missing) {
+#pragma unroll
+                for (int p = 0; p < PJ_AR_MAX_RANKS; ++p)
+                    if (missing & (1u << p)) w[p] = ld_relaxed_sys_u64(mine + (long long)p * a.n_pad + i);
+#pragma unroll
+                for (int p = 0; p < PJ_AR_MAX_RANKS; ++p)
+                    if ((missing & (1u << p)) && (unsigned)(w[p] >> 32) == e) missing &= ~(1u << p);
+            }
+            float acc = 0.0f;
+#pragma unroll
+            for (int p = 0; p < PJ_AR_MAX_RANKS; ++p)
+                if (p < a.world) acc += (p == a.rank && k == 0) ? own : __uint_as_float((unsigned)w[p]);
+            buf[i] = acc;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) *my_epoch = e;
+}
+
+cudaError_t launch_reduce_allreduce(const unsigned long long* peers, int rank, int world, const float* gpart, int n_parts,
+                                    long long n_theta, float* buf, long long n, cudaStream_t s) {
+    ArArgs a;
+    for (int p = 0; p < PJ_AR_MAX_RANKS; ++p) a.buf[p] = p < world ? peers[p] : 0ull;
+    a.self = peers[rank];
+    a.rank = rank;
+    a.world = world;
+    a.n = n;
+    a.n_pad = (n + 63) / 64 * 64;
+    const long long n_chunks = (n + 63) / 64;
+    const unsigned grid = (unsigned)(n_chunks < PJ_ARF_BLOCKS ? n_chunks : PJ_ARF_BLOCKS);
+    reduce_allreduce_kernel<<<grid, 256, 0, s>>>(a, gpart, n_parts, n_theta, buf);
+    return cudaGetLastError();
+}
+
 }  // namespace pj
 
 extern "C" {
+
+int64_t pj_backward_allreduce_bytes(int64_t n_floats, int32_t world) {
+    const int64_t n_pad = (n_floats + 63) / 64 * 64;
+    return PJ_ARF_HEADER_BYTES + 2 * (int64_t)(world < 1 ? 1 : world) * n_pad * 8;
+}
 
 int64_t pj_allreduce_bytes(int64_t n_floats) {
     const int64_t n_pad = (n_floats + 3) / 4 * 4;
@@ -104,6 +218,7 @@ int pj_allreduce_oneshot(const uint64_t* peer_buffers, int32_t rank, int32_t wor
     if (!peer_buffers || !in || !out || world < 1 || world > PJ_AR_MAX_RANKS || rank < 0 || rank >= world || n_floats < 1) return -1;
     pj::ArArgs a;
     for (int p = 0; p < PJ_AR_MAX_RANKS; ++p) a.buf[p] = p < world ? peer_buffers[p] : 0ull;
+    a.self = peer_buffers[rank];
     a.rank = rank;
     a.world = world;
     a.n = n_floats;

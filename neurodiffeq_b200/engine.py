@@ -78,8 +78,12 @@ def load_library():
     lib.pj_forward_jit.argtypes = [vp] + list(lib.pj_forward.argtypes)
     lib.pj_forward_train_jit.argtypes = [vp, ctypes.POINTER(PjSpec), vp, i32, vp, i32, ctypes.POINTER(vp), i64, vp, f32, vp, vp,
                                          vp, ctypes.c_size_t, vp]
+    lib.pj_backward_allreduce.argtypes = [ctypes.POINTER(PjSpec), ctypes.POINTER(vp), i64, vp, vp, i64, vp, ctypes.c_size_t,
+                                          ctypes.POINTER(ctypes.c_uint64), i32, i32, vp]
+    lib.pj_backward_allreduce_bytes.argtypes = [i64, i32]
+    lib.pj_backward_allreduce_bytes.restype = i64
     for fn in (lib.pj_sizes, lib.pj_pack, lib.pj_forward, lib.pj_forward_train, lib.pj_backward, lib.pj_forward_jit,
-               lib.pj_forward_train_jit):
+               lib.pj_forward_train_jit, lib.pj_backward_allreduce):
         fn.restype = ctypes.c_int
     if lib.pj_abi_version() != 2:
         raise RuntimeError("libpinnjet.so ABI version mismatch")
@@ -89,7 +93,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ("pj_abi_version", "pj_last_error", "pj_sizes", "pj_plan_info", "pj_pack", "pj_forward", "pj_forward_train",
                     "pj_backward", "pj_allreduce_bytes", "pj_allreduce_oneshot", "pj_sample", "pj_adam_step", "pj_forward_jit",
-                    "pj_forward_train_jit")
+                    "pj_forward_train_jit", "pj_backward_allreduce_bytes", "pj_backward_allreduce")
 
 
 def _check(rc, what):
@@ -415,10 +419,14 @@ class FusedProblem:
         self.kernel_launches += 2 if want_sumsq else 1
         return u, r, (self.sumsq if want_sumsq else None)
 
-    def residual_grad(self, coords, n_global=None, want_residual=False, rbar=None, sumsq_out=None, repack=True, ubar=None):
+    def residual_grad(self, coords, n_global=None, want_residual=False, rbar=None, sumsq_out=None, repack=True, ubar=None,
+                      reducer=None):
         """K1(train)+K2+K2b: ``grad`` += d/dtheta mean(r^2) (or of the caller's loss when ``rbar`` = dL/dr [n_eq, N] and,
         for losses that also depend on the functions, ``ubar`` = dL/du [n_funcs, N] are given);
-        returns (sum r^2 device tensor, residual or None).  mean(r^2) = sumsq / (N_global * n_eq)."""
+        returns (sum r^2 device tensor, residual or None).  mean(r^2) = sumsq / (N_global * n_eq).
+        ``reducer`` (a ``parallel.GradBufReducer`` built for ``self.gradbuf``): afterwards ``gradbuf`` = [grad | sum r^2]
+        holds the SUM over the ranks -- K2b and the collective as one kernel when the reducer offers it
+        (``pj_backward_allreduce``), K2b followed by the reducer otherwise."""
         n = coords[0].numel()
         if ubar is not None:
             self.enable_function_adjoints()      # may enlarge spec.n_slots: before any size / plan query
@@ -461,8 +469,19 @@ class FusedProblem:
                    "pj_forward_train")
         if self._skips:
             self._accumulate_shortcut_grads(keep, n)
-        _check(self.lib.pj_backward(ctypes.byref(self.spec), ptrs, n, self.pack_buf.data_ptr(), self.grad.data_ptr(),
-                                    self.workspace.data_ptr(), self.workspace.numel(), self._stream()), "pj_backward")
+        if reducer is not None and sumsq_out is not self.sumsq:
+            raise ValueError("residual_grad(reducer=...) sums self.gradbuf: pass sumsq_out=self.sumsq")
+        if reducer is not None and reducer.fused_args is not None:
+            peers, rank, world = reducer.fused_args
+            _check(self.lib.pj_backward_allreduce(ctypes.byref(self.spec), ptrs, n, self.pack_buf.data_ptr(),
+                                                  self.gradbuf.data_ptr(), self.gradbuf.numel() - self.grad.numel(),
+                                                  self.workspace.data_ptr(), self.workspace.numel(), peers, rank, world,
+                                                  self._stream()), "pj_backward_allreduce")
+        else:
+            _check(self.lib.pj_backward(ctypes.byref(self.spec), ptrs, n, self.pack_buf.data_ptr(), self.grad.data_ptr(),
+                                        self.workspace.data_ptr(), self.workspace.numel(), self._stream()), "pj_backward")
+            if reducer is not None:
+                reducer(self.gradbuf)
         self.kernel_launches += 4
         return sumsq_out, r
 

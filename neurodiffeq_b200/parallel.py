@@ -32,11 +32,15 @@ class GradBufReducer:
     """SUM of one flat float32 buffer over the ranks, in place; ``mode`` says how: ``"single"`` (no process group),
     ``"oneshot-nvlink"`` (one launch of ``pj_allreduce_oneshot``: every rank reads its peers' copies over NVLink and adds
     them in rank order -- bit-identical results everywhere, CUDA-graph capturable) or ``"process-group"``
-    (``dist.all_reduce``).  ``PINNJET_ALLREDUCE=nccl`` forces the last one."""
+    (``dist.all_reduce``).  ``PINNJET_ALLREDUCE=nccl`` forces the last one.
+
+    ``fused_args`` (one-shot mode only, else ``None``): ``(peer pointers, rank, world)`` of a SECOND symmetric buffer, for
+    ``pj_backward_allreduce`` -- the reverse kernel's partial reduction and this collective as one launch
+    (``FusedProblem.residual_grad(reducer=...)``); ``PINNJET_FUSED_AR=0`` keeps the two launches."""
 
     def __init__(self, buf, dist=None):
         dist = dist or torch.distributed
-        self.dist, self.mode, self.why = dist, "single", ""
+        self.dist, self.mode, self.why, self.fused_args = dist, "single", "", None
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
             return
         self.mode = "process-group"
@@ -69,9 +73,18 @@ class GradBufReducer:
                 raise RuntimeError("symmetric-memory world size mismatch")
             self._ptrs = (ctypes.c_uint64 * world)(*[int(p) for p in self._hdl.buffer_ptrs])
             self._rank, self._world, self._n, self._lib = dist.get_rank(), world, n, lib
+            fused = None
+            if os.environ.get("PINNJET_FUSED_AR", "1") != "0":   # every rank reads the same environment: same rendezvous count
+                from . import engine as _e
+                lib = _e.load_library()
+                words_f = int(lib.pj_backward_allreduce_bytes(n, world)) // 4
+                self._sym_f = symm.empty(words_f, dtype=torch.float32, device=buf.device)
+                self._sym_f.zero_()
+                self._hdl_f = symm.rendezvous(self._sym_f, group.group_name)
+                fused = ((ctypes.c_uint64 * world)(*[int(p) for p in self._hdl_f.buffer_ptrs]), self._rank, world)
             torch.cuda.synchronize(buf.device)
             dist.barrier()                      # every rank's flags are zero before anyone signals
-            self.mode = "oneshot-nvlink"
+            self.mode, self.fused_args = "oneshot-nvlink", fused
         except Exception as exc:  # noqa: BLE001  -- no peer access / symmetric memory: the process group still works
             self.why = f"{type(exc).__name__}: {exc}"
 

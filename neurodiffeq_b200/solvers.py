@@ -563,9 +563,8 @@ class BaseSolver:
             lo, hi, n_glob = st.bounds["train"]
             st.samplers["train"].sample_into(st.coords["train"], lo, hi - lo)
             fp.gradbuf.zero_()
-            fp.residual_grad(st.coords["train"], n_global=n_glob, sumsq_out=fp.sumsq)   # K0, K1, finalize, K2, K2b
-            if st.reducer is not None:
-                st.reducer(fp.gradbuf)
+            # K0, K1, finalize, K2, K2b; under data parallelism K2b and the collective are one kernel (pj_backward_allreduce)
+            fp.residual_grad(st.coords["train"], n_global=n_glob, sumsq_out=fp.sumsq, reducer=st.reducer)
             train_loss = fp.sumsq / float(n_glob * fp.n_eq)
             if n_valid == 0:   # lowest loss / best parameters from the training loss, before the optimizer step (reference
                 opt._step_fused(train_loss, st.best_loss, st.best_theta)       # solvers.py:411-412), in the Adam launch

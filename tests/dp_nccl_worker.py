@@ -39,6 +39,7 @@ def main():
     shard = fp.gradbuf.clone()
     all_reduce_gradbuf(fp.gradbuf, dist)
     torch.cuda.synchronize()
+    nccl_sum = fp.gradbuf.clone()
     grad_rel = float((fp.gradbuf[:-1] - full[:-1]).norm() / full[:-1].norm())
     sumsq_rel = float(abs(fp.gradbuf[-1] - full[-1]) / full[-1])
     # the hand-written one-shot NVLink all-reduce: same sum as NCCL's (rank order vs. NCCL's order: fp32 rounding), identical
@@ -53,7 +54,7 @@ def main():
             work.copy_(shard * float(it + 1))
             red2(work)
             torch.cuda.synchronize()
-            ref = fp.gradbuf * float(it + 1)
+            ref = nccl_sum * float(it + 1)
             errs.append(float((work - ref).norm() / ref.norm()))
             g = [torch.empty_like(work) for _ in range(world)]
             dist.all_gather(g, work)
@@ -73,9 +74,51 @@ def main():
             static.copy_(shard * float(it + 2))
             graph.replay()
             torch.cuda.synchronize()
-            ref = fp.gradbuf * float(it + 2)
+            ref = nccl_sum * float(it + 2)
             errs.append(float((static - ref).norm() / ref.norm()))
         oneshot.update(max_rel_err_vs_nccl=max(errs), ranks_identical=same)
+        # K2b + collective as ONE kernel (pj_backward_allreduce): same arithmetic in the same order as K2b followed by the
+        # one-shot kernel -> bit-identical to it; back to back, accumulating into a non-zero buffer, and in a replayed graph
+        oneshot["fused"] = red.fused_args is not None
+        if red.fused_args is not None:
+            shard_coords = [c[lo:hi].contiguous() for c in coords]
+            two_step = shard.clone()
+            red(two_step)
+            torch.cuda.synchronize()
+            fused_equal, fused_same, fused_rel = True, True, 0.0
+            for it in range(5):
+                fp.gradbuf.zero_()
+                fp.residual_grad(shard_coords, n_global=n, sumsq_out=fp.sumsq, reducer=red)
+                torch.cuda.synchronize()
+                fused_equal = fused_equal and bool(torch.equal(fp.gradbuf, two_step))
+                fused_rel = max(fused_rel, float((fp.gradbuf - two_step).norm() / two_step.norm()))
+                g = [torch.empty_like(fp.gradbuf) for _ in range(world)]
+                dist.all_gather(g, fp.gradbuf)
+                fused_same = fused_same and all(bool(torch.equal(x, g[0])) for x in g)
+            fp.gradbuf.fill_(0.25)                      # accumulation: every rank's previous content is summed along
+            fp.residual_grad(shard_coords, n_global=n, sumsq_out=fp.sumsq, reducer=red)
+            torch.cuda.synchronize()
+            acc_ref = two_step + 0.25 * world
+            fused_acc = float((fp.gradbuf - acc_ref).norm() / acc_ref.norm())
+            graph = torch.cuda.CUDAGraph()
+
+            def fused_body():
+                fp.gradbuf.zero_()
+                fp.residual_grad(shard_coords, n_global=n, sumsq_out=fp.sumsq, reducer=red)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fused_body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            dist.barrier()
+            with torch.cuda.graph(graph):
+                fused_body()
+            for it in range(3):
+                graph.replay()
+                torch.cuda.synchronize()
+                fused_equal = fused_equal and bool(torch.equal(fp.gradbuf, two_step))
+            oneshot.update(fused_rel_vs_two_step=fused_rel, fused_equals_two_step=fused_equal, fused_ranks_identical=fused_same, fused_accumulate_rel=fused_acc)
 
     # Solver.fit in lock-step: the ranks end with identical parameters, equal to a single-process run of the same problem
     wl, solver, snets, coords_np = make_solver(key, 3001)
