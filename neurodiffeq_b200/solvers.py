@@ -27,6 +27,7 @@ import torch.nn as nn
 
 from .conditions import BaseCondition
 from .engine import FusedProblem
+from .eager import build_problem
 from ._compat import renamed_arguments
 from .losses import _losses, h1_rows, h1_semi_rows
 from .generators import Generator1D, Generator2D, GeneratorSpherical, SamplerGenerator
@@ -68,7 +69,7 @@ def _unique(params):
 class BaseSolution:
     """Callable solution ``u(*coords)`` evaluated by the forward kernel (reference solvers.py:650-720)."""
 
-    def __init__(self, nets, conditions, n_coords, coords_for_condition=None, enforce=None):
+    def __init__(self, nets, conditions, n_coords, coords_for_condition=None, enforce=None, device=None):
         if nets is None:
             raise RuntimeError("The nets cannot be None, check if you disabled validation "
                                "and used `best`=True with `get_solution` / `get_residual`")
@@ -77,11 +78,14 @@ class BaseSolution:
         self._n_coords = n_coords
         self._cfc = coords_for_condition
         self._enforce = enforce
+        self._device = device
         self._problem = None
 
     def _fused(self):
         if self._problem is None:
-            self._problem = FusedProblem(self.nets, self.conditions, None, self._n_coords, self._cfc, enforce=self._enforce)
+            # the fused forward kernel, or the autograd path for what the tracer refuses (eager.py)
+            self._problem = build_problem(FusedProblem, self.nets, self.conditions, None, self._n_coords, self._cfc,
+                                          device=self._device, enforce=self._enforce)
         return self._problem
 
     @renamed_arguments(as_type="to_numpy")                          # reference solvers.py:681
@@ -96,6 +100,8 @@ class BaseSolution:
         coords = [c if isinstance(c, torch.Tensor) else torch.as_tensor(np.asarray(c)) for c in coords]
         shape = coords[0].shape
         fp = self._fused()
+        if not fp.parameters_linked():   # live networks (get_solution(copy=False, best=False)) whose solver trained on since:
+            fp.relink()                  # adopt the parameters' current values, like the reference's live nets
         u, _, _ = fp.forward([c.reshape(-1) for c in coords], want_u=True, want_residual=False)
         us = _functions(fp.tp, u, None if no_reshape else shape)
         if to_numpy:
@@ -158,15 +164,18 @@ class BaseSolver:
         self.n_coords = n_coords
         self._set_loss_fn(loss_fn)      # before tracing: the 'h1' loss adds derivative rows to the traced residuals
         if self._h1 == "semi":   # loss rows: derivative rows only; the user's residuals ride along as auxiliary outputs
-            self.problem = FusedProblem(self.nets, self.conditions, h1_semi_rows(self._traced_diff_eqs, self.n_funcs),
-                                        n_coords, coords_for_condition=self._coords_for_condition, device=device,
-                                        aux_outputs=self._traced_diff_eqs, enforce=self.compute_func_val)
+            self.problem = build_problem(FusedProblem, self.nets, self.conditions,
+                                         h1_semi_rows(self._traced_diff_eqs, self.n_funcs),
+                                         n_coords, coords_for_condition=self._coords_for_condition, device=device,
+                                         aux_outputs=self._traced_diff_eqs, enforce=self.compute_func_val)
             self.n_eq = len(self.problem.tp.aux_rows)
         else:
-            self.problem = FusedProblem(self.nets, self.conditions,
-                                        self._h1_rows if self._h1 else self._traced_diff_eqs, n_coords,
-                                        coords_for_condition=self._coords_for_condition, device=device,
-                                        enforce=self.compute_func_val)
+            # the fused engine (trace once -> kernels); what its tracer / planner refuses runs on the autograd path with one
+            # warning (eager.py)
+            self.problem = build_problem(FusedProblem, self.nets, self.conditions,
+                                         self._h1_rows if self._h1 else self._traced_diff_eqs, n_coords,
+                                         coords_for_condition=self._coords_for_condition, device=device,
+                                         enforce=self.compute_func_val)
             self.n_eq = self.problem.n_eq - (n_coords if self._h1 else 0)     # the user's equations
         self.device = self.problem.device
         if jit or os.environ.get("PINNJET_JIT") == "1":   # opt-in: the residual programs compiled into the forward kernel
@@ -511,6 +520,8 @@ class BaseSolver:
         """None if an epoch of this solver can run as one captured graph, else the reason it cannot."""
         from .device_sampling import describe
         from .optim import FlatAdam
+        if getattr(self.problem, "is_eager", False):
+            return "the problem runs on the autograd path (" + self.problem.reason + ")"
         if self._custom_loss is not None:
             return "the loss needs autograd on the host (custom loss_fn / additional_loss)"
         if self.metrics_fn:
@@ -672,7 +683,7 @@ class BaseSolver:
         elif best:
             warnings.warn("copy=False with best=True returns a copy of the best networks", RuntimeWarning)
         return self._solution_class()(nets, conditions, self.n_coords, self._coords_for_condition,
-                                      enforce=self.compute_func_val)
+                                      enforce=self.compute_func_val, device=self.device)
 
     def get_residuals(self, *coords, to_numpy=False, best=True, no_reshape=False):
         coords = [c if isinstance(c, torch.Tensor) else torch.as_tensor(np.asarray(c)) for c in coords]

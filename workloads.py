@@ -221,6 +221,38 @@ def _resnet(nd):
                     make_nets, make_conditions, diff_eqs, 1, 4096, _fcnn_flops((2, 32, 32, 1), 4), None)
 
 
+def _third_order(nd):
+    """u(3) + u(1) = 0, u(0) = 1, u(1)(0) = 0: order-3 derivative of a network output -- beyond the order-2 jets of the fused
+    kernels (the reference nests diff to order 3 and more: tests/test_operators_identities.py:124-131); autograd path."""
+    def make_nets():
+        return [nd.FCNN(n_input_units=1, n_output_units=1, hidden_units=(16, 16))]
+
+    def make_conditions():
+        return [nd.IVP(t_0=0.0, u_0=1.0, u_0_prime=0.0)]
+
+    def diff_eqs(u, t):
+        return [nd.diff(u, t, order=3) + nd.diff(u, t)]
+
+    return Workload("y1_third_order_ode", "Solver1D", ("t",), ((0.0, 2.0),), [((1, 16, 16, 1), "tanh")], make_nets,
+                    make_conditions, diff_eqs, 1, 512, _fcnn_flops((1, 16, 16, 1), 4), None)
+
+
+def _softplus_net(nd):
+    """du/dt + u = 0 with a Softplus network: an activation without a jet rule in the kernels (like the reference's Swish /
+    APTx, networks.py:155-208); autograd path."""
+    def make_nets():
+        return [nd.FCNN(n_input_units=1, n_output_units=1, hidden_units=(16, 16), actv=torch.nn.Softplus)]
+
+    def make_conditions():
+        return [nd.IVP(t_0=0.0, u_0=1.0)]
+
+    def diff_eqs(u, t):
+        return [nd.diff(u, t) + u]
+
+    return Workload("y2_softplus_decay", "Solver1D", ("t",), ((0.0, 2.0),), [((1, 16, 16, 1), "softplus")], make_nets,
+                    make_conditions, diff_eqs, 1, 512, _fcnn_flops((1, 16, 16, 1), 2), None)
+
+
 _EXTRA = {
     "x1": lambda nd: _heat(nd, "x1_heat_dirichlet_neumann", "right"),
     "x2": lambda nd: _heat(nd, "x2_heat_neumann_dirichlet", "left"),
@@ -236,6 +268,10 @@ _BUILDERS = {"c1": _c1, "c2": _c2, "c3": _c3, "c4": _c4, "c5": _c5}
 NAMES = tuple(_BUILDERS)          # BASELINE.json configs
 EXTRA_NAMES = tuple(_EXTRA)       # widened condition family
 _BUILDERS.update(_EXTRA)
+# problems the fused engine refuses: they run on the autograd path (neurodiffeq_b200/eager.py)
+_FALLBACK = {"y1": _third_order, "y2": _softplus_net}
+FALLBACK_NAMES = tuple(_FALLBACK)
+_BUILDERS.update(_FALLBACK)
 
 
 def build(nd, key):
