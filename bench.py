@@ -289,8 +289,7 @@ def strong_scaling_leg(key, n_global, world, rank, dev, steps, warmup, flush_l2,
     reducer = GradBufReducer(fp.gradbuf, dist) if world > 1 else None
 
     def body():
-        fp.gradbuf.zero_()
-        fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq, reducer=reducer)
+        fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq, reducer=reducer, zero_gradbuf=True)
 
     for _ in range(max(warmup, 3)):
         body()
@@ -396,10 +395,10 @@ def main():
     reducer, align = None, None
 
     def step_body():
-        fp.gradbuf.zero_()                                # optimizer.zero_grad() + loss accumulator
-        # N > 1: SUM of [grad | sum r^2] over the ranks (parallel.GradBufReducer) -- K2b and the one-shot NVLink collective
+        # K0 re-packs theta and clears [grad | sum r^2] (optimizer.zero_grad() + loss accumulator) in one launch; the loss
+        # finalisation happens inside K1 (last-warp ticket).  N > 1: SUM of [grad | sum r^2] over the ranks (parallel.GradBufReducer) -- K2b and the one-shot NVLink collective
         # as ONE kernel (pj_backward_allreduce) when peer memory is available, K2b + the process group's all-reduce otherwise
-        fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq, reducer=reducer)
+        fp.residual_grad(coords, n_global=n_global, sumsq_out=fp.sumsq, reducer=reducer, zero_gradbuf=True)
 
     if world > 1:
         from neurodiffeq_b200.parallel import GradBufReducer
@@ -445,8 +444,8 @@ def main():
         else:
             step_body()
 
-    launches_per_step = 1 + 5   # gradbuf fill (torch) is not ours; pack, K1, loss-finalize, K2, K2b are
-    ours_per_step = 5 + (1 if (reducer is not None and reducer.mode == "oneshot-nvlink" and not fused_collective) else 0)
+    # pack (+ clear), K1 (+ loss finalisation), K2, K2b (or K2b + collective as one kernel); no torch launch inside the step
+    ours_per_step = 4 + (1 if (reducer is not None and reducer.mode == "oneshot-nvlink" and not fused_collective) else 0)
 
     # ---- timed region: K steps, L2 flushed before each, CUDA events per step, max over ranks -------------------------
     if world > 1:
@@ -590,7 +589,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "r02", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(args.workload, {}).get(k1_name, {}).get("dram_bytes")
+            traffic = json.load(f).get(args.workload, {}).get("pj_k1_jit" if (jit_on and tc_fwd) else k1_name, {}).get("dram_bytes")
     roofline = {
         "kernel": k1_name + (" specialised (pj_k1_jit: residual programs compiled in)" if jit_on else "") +
                   " (forward + jets + residual program)",
@@ -653,7 +652,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl.name}: {wl.solver}, nets {wl.nets_spec}, {n} points/GPU, "
-                                   f"residual+grad step = pack+K1+finalize+K2+K2b"
+                                   f"residual+grad step = K0 (pack + clear grad) + K1 (+ loss finalisation) + K2 + K2b"
                                    + (f" + all-reduce of [grad|loss] ({reducer.mode}"
                                       f"{', fused with K2b' if fused_collective else ''})" if world > 1 else ""),
                        "points_per_gpu": n, "global_points": n_global, "tile_points": info["T"],

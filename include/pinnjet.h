@@ -19,6 +19,8 @@
  *   grad_theta  : same layout; pj_backward ACCUMULATES (+=) like loss.backward() (solvers.py:360-362, 393)
  *   u_out       : float[n_funcs][N]   re-parameterised functions  (conditions.py:41-57)
  *   resid_out   : float[n_eq][N]      residuals of diff_eqs       (solvers.py:380-381, transposed: SoA)
+ *   workspace   : caller-owned scratch of pj_sizes() bytes; its first 4 KB (per-CTA loss partials + the ticket of the
+ *                 in-kernel loss finalisation) must be ZERO before the first call -- the kernels leave the ticket zero
  *   program     : int32[len][4] bytecode produced by neurodiffeq_b200/symbolic.py (op,dst,a,b)
  *   prog_w      : optional weight program (coords -> wl weights per net) of the combined second-order channel; NULL/0
  *                 when spec->wl == 0
@@ -97,6 +99,10 @@ int pj_plan_info(const PjSpec* spec, int64_t n_points, int64_t* out, int32_t n_o
 /* Re-layout the live parameters for the kernels (K-major + padded copies).  Call after every optimizer step.
  * Replaces nothing in the reference (its weights are read in place by aten::addmm); cost: one tiny launch. */
 int pj_pack(const PjSpec* spec, const float* theta /*device*/, float* theta_pack /*device*/, void* stream);
+/* pj_pack that also clears zero_buf[0, n_zero) in the same launch: the step's optimizer.zero_grad() (solvers.py:361-362) and
+ * loss accumulator -- the [grad_theta | sum r^2] buffer -- without a fill launch of its own. */
+int pj_pack_zero(const PjSpec* spec, const float* theta /*device*/, float* theta_pack /*device*/, float* zero_buf /*device*/,
+                 int64_t n_zero, void* stream);
 
 /* Inference / validation: u and residual at N points, optional sum of squared residuals.
  * Replaces  funcs = cond.enforce(net, *coords); residuals = diff_eqs(*funcs, *coords)
@@ -161,7 +167,7 @@ int pj_allreduce_oneshot(const uint64_t* peer_buffers /*host array [world]*/, in
  * No flag, fence or barrier between the ranks: the critical path is ONE one-way NVLink store (the stand-alone kernel needs
  * a flag one way and the data back).  Same symmetric-buffer rules as pj_allreduce_oneshot, but its OWN buffer of
  * pj_backward_allreduce_bytes(n_theta + n_tail, world) bytes, zero-initialised. */
-#define PJ_ARF_BLOCKS 160
+#define PJ_ARF_BLOCKS 320
 #define PJ_ARF_HEADER_BYTES 8192   /* one epoch counter per block; the {epoch, value} slots start here */
 int64_t pj_backward_allreduce_bytes(int64_t n_floats, int32_t world);
 int pj_backward_allreduce(const PjSpec* spec, const float* const* coords, int64_t n_points, const float* theta_pack,

@@ -5,6 +5,7 @@
 
 #include <cstdlib>
 #include <dlfcn.h>
+#include <cuda.h>   // types of the driver API only (CUlaunchConfig): the entry point is resolved with dlsym, nothing links against libcuda
 #include <cuda_bf16.h>
 
 #include "pinnjet_common.cuh"
@@ -362,7 +363,7 @@ static int make_plan_ntc(const PjSpec& sp, long long N, int prog_len, int prog_w
                                           pl.k1_bytes, pl.k2_bytes);
         pl.grid = pl.n_tiles1 < sms * o1 ? pl.n_tiles1 : sms * o1;
         pl.grid_bwd = pl.n_tiles < sms * o2 ? pl.n_tiles : sms * o2;
-        if (pl.grid > 640) pl.grid = 640;   // loss partials live in the first 2.5 KB of the workspace
+        if (pl.grid > 639) pl.grid = 639;   // loss partials live in the first 2.5 KB of the workspace (word 639: finalisation ticket)
         *occ_min = pl.tc_bwd ? 2 : o2;      // (the tensor-core plan does not depend on the CTA shape: accept it at once)
     }
     // ---- workspace ----
@@ -403,9 +404,21 @@ struct PackArgs {
     Plan plan;
 };
 
-__global__ void pack_kernel(const __grid_constant__ PackArgs A, const float* __restrict__ theta, float* __restrict__ pack) {
+// Grid (n_nets * PJ_MAX_LINEAR, PACK_PARTS): block (x, y) does every PACK_PARTS-th element of Linear x % PJ_MAX_LINEAR of net
+// x / PJ_MAX_LINEAR (4 CTAs per layer instead of 1: the kernel is latency bound).  All blocks together also clear
+// zero_buf[0, n_zero) when given (pj_pack_zero: the optimizer.zero_grad() of the step rides along instead of a fill launch).
+constexpr int PACK_PARTS = 4;
+__global__ void pack_kernel(const __grid_constant__ PackArgs A, const float* __restrict__ theta, float* __restrict__ pack,
+                            float* __restrict__ zero_buf, long long n_zero) {
     const PjSpec& sp = A.spec;
     const Plan& pl = A.plan;
+    pdl_launch_dependents();   // the forward kernel's CTAs may become resident now; they wait for this grid before reading `pack`
+    const int part = blockIdx.y, nparts = gridDim.y;
+    if (zero_buf) {
+        const long long nthreads = (long long)gridDim.x * gridDim.y * blockDim.x;
+        for (long long i = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < n_zero; i += nthreads)
+            zero_buf[i] = 0.0f;
+    }
     const int n = blockIdx.x / PJ_MAX_LINEAR, l = blockIdx.x % PJ_MAX_LINEAR;
     if (n >= sp.n_nets) return;
     const PjNet& net = sp.net[n];
@@ -414,7 +427,7 @@ __global__ void pack_kernel(const __grid_constant__ PackArgs A, const float* __r
     const int fin = net.width[l], fout = net.width[l + 1];
     const float* W = theta + net.w_off[l];
     const float* b = theta + net.b_off[l];
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x + part * blockDim.x, nt = blockDim.x * nparts;   // this block's share of every loop
     if (l == 0) {
         const int hp1 = pl.hp[n][1];
         float* wt = pack + pl.s_wt0[n];
@@ -537,25 +550,44 @@ int pj_plan_info(const PjSpec* spec, int64_t n_points, int64_t* out, int32_t n_o
     return 0;
 }
 
-int pj_pack(const PjSpec* spec, const float* theta, float* theta_pack, void* stream) {
+static int pack_impl(const PjSpec* spec, const float* theta, float* theta_pack, float* zero_buf, long long n_zero, void* stream) {
     if (!spec || !theta || !theta_pack) return fail(-1, "null argument");
     PackArgs a;
     a.spec = *spec;
     if (int rc = make_plan(*spec, 1, 0, a.plan)) return rc;
-    pack_kernel<<<spec->n_nets * PJ_MAX_LINEAR, 256, 0, (cudaStream_t)stream>>>(a, theta, theta_pack);
+    pack_kernel<<<dim3(spec->n_nets * PJ_MAX_LINEAR, PACK_PARTS), 256, 0, (cudaStream_t)stream>>>(a, theta, theta_pack, zero_buf, n_zero);
     return check_cuda(cudaGetLastError(), "pack launch");
+}
+
+int pj_pack(const PjSpec* spec, const float* theta, float* theta_pack, void* stream) {
+    return pack_impl(spec, theta, theta_pack, nullptr, 0, stream);
+}
+
+int pj_pack_zero(const PjSpec* spec, const float* theta, float* theta_pack, float* zero_buf, int64_t n_zero, void* stream) {
+    if (!zero_buf || n_zero < 1) return fail(-1, "pj_pack_zero: nothing to clear");
+    return pack_impl(spec, theta, theta_pack, zero_buf, n_zero, stream);
 }
 
 // The specialised forward kernel (neurodiffeq_b200/jit.py) arrives as a CUfunction handle of a module the caller loaded:
 // launched through the driver API, resolved lazily so that the library itself does not link against libcuda.
-typedef int (*CuLaunchKernel)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**, void**);
-static CuLaunchKernel cu_launch_kernel() {
-    static CuLaunchKernel fn = nullptr;
+// (cuLaunchKernelEx: the launch carries the programmatic-dependent-launch attribute like the built-in kernels' launches.)
+typedef CUresult (*CuLaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**);
+static CuLaunchKernelEx cu_launch_kernel_ex() {
+    static CuLaunchKernelEx fn = nullptr;
     if (!fn) {
         void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
-        if (h) fn = reinterpret_cast<CuLaunchKernel>(dlsym(h, "cuLaunchKernel"));
+        if (h) fn = reinterpret_cast<CuLaunchKernelEx>(dlsym(h, "cuLaunchKernelEx"));
     }
     return fn;
+}
+
+// PINNJET_FOLD_FINALIZE=0 brings the separate loss_finalize launch back (A/B, bring-up)
+static bool fold_finalize() {
+    static const int on = [] {
+        const char* e = getenv("PINNJET_FOLD_FINALIZE");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return on != 0;
 }
 
 static int run_k1(const PjSpec* spec, const int32_t* prog, int32_t prog_len, const int32_t* prog_w, int32_t prog_w_len,
@@ -590,6 +622,8 @@ static int run_k1(const PjSpec* spec, const int32_t* prog, int32_t prog_len, con
     char* w = static_cast<char*>(ws);
     a.loss_part = reinterpret_cast<float*>(w + a.plan.ws_loss);
     a.dbg = a.loss_part + 640;   // tail of the 4 KB loss-partial block (only written by PJ_TIMING builds)
+    a.ticket = reinterpret_cast<unsigned*>(a.loss_part + 639);   // last-warp ticket of the in-kernel loss finalisation (zero between launches)
+    a.sumsq_out = fold_finalize() ? sumsq_out : nullptr;
     a.zj = mode == 1 ? reinterpret_cast<float*>(w + (a.plan.tc ? a.plan.ws_tcrec : a.plan.ws_zj)) : nullptr;
     a.zj_ffma = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_zj) : nullptr;
     a.seeds = mode == 1 ? reinterpret_cast<float*>(w + a.plan.ws_seed) : nullptr;
@@ -597,17 +631,31 @@ static int run_k1(const PjSpec* spec, const int32_t* prog, int32_t prog_len, con
     const SchemeEntry* e = find_scheme(spec->n1, spec->n2, spec->wl);
     if (jit_function) {   // the problem's own forward kernel: same arguments, same plan; then the record copy of the isolation mode
         if (!a.plan.tc) return fail(-2, "the specialised forward kernel exists for the tensor-core path only");
-        CuLaunchKernel launch = cu_launch_kernel();
-        if (!launch) return fail(-4, "libcuda.so.1 / cuLaunchKernel not available");
+        CuLaunchKernelEx launch = cu_launch_kernel_ex();
+        if (!launch) return fail(-4, "libcuda.so.1 / cuLaunchKernelEx not available");
         void* params[1] = {&a};
-        const int rc = launch(jit_function, (unsigned)a.plan.grid, 1, 1, 640, 1, 1, (unsigned)a.plan.k1_bytes, stream, params, nullptr);
-        if (rc != 0) return fail(-5, "cuLaunchKernel of the specialised forward kernel failed (%d)", rc);
+        CUlaunchConfig cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDimX = (unsigned)a.plan.grid;
+        cfg.gridDimY = cfg.gridDimZ = 1;
+        cfg.blockDimX = 640;
+        cfg.blockDimY = cfg.blockDimZ = 1;
+        cfg.sharedMemBytes = (unsigned)a.plan.k1_bytes;
+        cfg.hStream = (CUstream)stream;
+        CUlaunchAttribute attr[1];
+        memset(attr, 0, sizeof(attr));
+        attr[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+        attr[0].value.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        const int rc = (int)launch(&cfg, (CUfunction)jit_function, params, nullptr);
+        if (rc != 0) return fail(-5, "cuLaunchKernelEx of the specialised forward kernel failed (%d)", rc);
         if (mode == 1 && !a.plan.tc_bwd)
             if (int rc2 = check_cuda(launch_tc_relayout(a, (cudaStream_t)stream), "record re-layout")) return rc2;
     } else if (int rc = check_cuda((a.plan.tc ? e->k1tc : e->k1)(a, a.plan.grid, a.plan.k1_bytes, (cudaStream_t)stream), "forward launch")) {
         return rc;
     }
-    if (sumsq_out)
+    if (sumsq_out && !fold_finalize())
         return check_cuda(launch_loss_finalize(a.loss_part, a.plan.tc ? 2 * a.plan.grid : a.plan.grid, sumsq_out, (cudaStream_t)stream),
                           "loss finalize");
     return 0;

@@ -16,7 +16,9 @@
 // signalled the epoch in between, i.e. finished reading (stream order) -- no second barrier is needed.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/pinnjet.h"
+#include "pinnjet_common.cuh"   // red_group_sum / red_combine: the K2b arithmetic
 
 namespace pj {
 
@@ -97,9 +99,9 @@ __global__ void __launch_bounds__(256) allreduce_oneshot_kernel(const ArArgs a, 
 // (a scalar 8-byte store is single-copy atomic, also over NVLink): the receiver polls the word itself, so there is no flag,
 // no fence and no barrier between the ranks -- the critical path is one one-way store.
 //   symmetric buffer:  [epochs: PJ_ARF_BLOCKS x u32 | pad to PJ_ARF_HEADER_BYTES][slot 2][src rank world][n_pad] x u64
-//   chunk = 64 consecutive floats of [grad | tail]; CTA b owns chunks b, b + grid, ...; epoch e = CTA's counter + 1.
-//   phase 1 (per chunk): fold the per-CTA gradient partials in the fixed order of k2_reduce_kernel (4 groups of partials x
-//     64 parameters), add what the buffer already holds -> v; store {e, v} into slot[e & 1][my rank][i] of EVERY peer.
+//   chunk = RED_PARAMS (32) consecutive floats of [grad | tail]; CTA b owns chunks b, b + grid, ...; epoch e = CTA's counter + 1.
+//   phase 1 (per chunk): fold the per-CTA gradient partials in the fixed order of k2_reduce_kernel (red_group_sum /
+//     red_combine: 8 groups of partials x 32 parameters), add what the buffer already holds -> v; store {e, v} into slot[e & 1][my rank][i] of EVERY peer.
 //   phase 2 (per chunk): poll slot[e & 1][p][i] of the LOCAL buffer until its epoch is e, for every peer p (all loads in
 //     flight, re-polling only what is missing); sum in rank order (own value from the register) -> bit-identical on every
 //     rank and equal to K2b followed by the stand-alone kernel.
@@ -114,36 +116,26 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
     return v;
 }
 
-__global__ void __launch_bounds__(256) reduce_allreduce_kernel(const ArArgs a, const float* __restrict__ gpart, int n_parts,
-                                                               long long n_theta, float* buf) {
-    __shared__ float red[4][64];
-    const int b = blockIdx.x, tid = threadIdx.x, il = tid & 63, g = tid >> 6;
+__global__ void __launch_bounds__(RED_PARAMS * RED_GROUPS) reduce_allreduce_kernel(const ArArgs a, const float* __restrict__ gpart,
+                                                                                    int n_parts, long long n_theta, float* buf) {
+    __shared__ float red[RED_GROUPS][RED_PARAMS];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // programmatic dependent of the reverse kernel: its partials are complete
+    const int b = blockIdx.x, tid = threadIdx.x, il = tid & (RED_PARAMS - 1), g = tid / RED_PARAMS;
     unsigned char* me = reinterpret_cast<unsigned char*>(a.self);   // = a.buf[a.rank], without a dynamically indexed parameter
     unsigned* my_epoch = reinterpret_cast<unsigned*>(me) + b;
     const unsigned e = *my_epoch + 1u;
     const long long slot_words = (long long)a.world * a.n_pad;                                  // u64 words per slot
     const long long slot_off = PJ_ARF_HEADER_BYTES / 8 + (long long)(e & 1u) * slot_words;      // u64 words from the buffer start
-    const long long n_chunks = (a.n + 63) / 64;
-    const int per = (n_parts + 3) / 4, p_lo = g * per, p_hi = min(n_parts, p_lo + per);
+    const long long n_chunks = (a.n + RED_PARAMS - 1) / RED_PARAMS;
     float own = 0.0f;                       // the value of the CTA's first chunk stays in a register between the phases
     int k = 0;
     for (long long c = b; c < n_chunks; c += gridDim.x, ++k) {
-        const long long i = c * 64 + il;
-        float s = 0.0f;
-        if (i < n_theta) {
-            float s0 = 0.0f, s1 = 0.0f;
-            int p = p_lo;
-            for (; p + 1 < p_hi; p += 2) {
-                s0 += gpart[(size_t)p * n_theta + i];
-                s1 += gpart[(size_t)(p + 1) * n_theta + i];
-            }
-            if (p < p_hi) s0 += gpart[(size_t)p * n_theta + i];
-            s = s0 + s1;
-        }
-        red[g][il] = s;
+        const long long i = c * RED_PARAMS + il;
+        red[g][il] = i < n_theta ? red_group_sum(gpart, n_parts, n_theta, i, g) : 0.0f;
         __syncthreads();
         if (g == 0 && i < a.n) {
-            const float v = buf[i] + ((red[0][il] + red[1][il]) + (red[2][il] + red[3][il]));
+            const float v = buf[i] + red_combine(red, il);
             const unsigned long long word = ((unsigned long long)e << 32) | (unsigned long long)__float_as_uint(v);
 #pragma unroll
             for (int p = 0; p < PJ_AR_MAX_RANKS; ++p)
@@ -158,7 +150,7 @@ __global__ void __launch_bounds__(256) reduce_allreduce_kernel(const ArArgs a, c
         const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(me) + slot_off;
         k = 0;
         for (long long c = b; c < n_chunks; c += gridDim.x, ++k) {
-            const long long i = c * 64 + il;
+            const long long i = c * RED_PARAMS + il;
             if (i >= a.n) continue;
             unsigned long long w[PJ_AR_MAX_RANKS];
             unsigned missing = 0;
@@ -193,10 +185,19 @@ cudaError_t launch_reduce_allreduce(const unsigned long long* peers, int rank, i
     a.world = world;
     a.n = n;
     a.n_pad = (n + 63) / 64 * 64;
-    const long long n_chunks = (n + 63) / 64;
+    const long long n_chunks = (n + pj::RED_PARAMS - 1) / pj::RED_PARAMS;
     const unsigned grid = (unsigned)(n_chunks < PJ_ARF_BLOCKS ? n_chunks : PJ_ARF_BLOCKS);
-    reduce_allreduce_kernel<<<grid, 256, 0, s>>>(a, gpart, n_parts, n_theta, buf);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(RED_PARAMS * RED_GROUPS);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    const char* env = getenv("PINNJET_PDL");
+    cfg.attrs = attr;
+    cfg.numAttrs = (env && env[0] == '1') ? 1 : 0;   // opt-in, see pdl_enabled() in pinnjet_common.cuh
+    return cudaLaunchKernelEx(&cfg, reduce_allreduce_kernel, a, gpart, n_parts, n_theta, buf);
 }
 
 }  // namespace pj

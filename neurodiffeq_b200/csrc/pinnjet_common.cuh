@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/pinnjet.h"
 
 #ifndef PJ_USE_FFMA2
@@ -17,6 +18,35 @@
 #endif
 
 namespace pj {
+
+// PINNJET_PDL=1 switches programmatic dependent launch between the kernels of a step on.  Off by default: measured on B200
+// (profiles/r02/bench_c2_v6.json vs bench_c2_nopdl_v6.json, same for C5) it does not pay -- inside a CUDA graph the kernel-to-
+// kernel gaps are already ~1 us and the early-resident dependents cost more than they hide (C2 0.1121 vs 0.1099 ms/step,
+// C5 0.2266 vs 0.2204).
+inline bool pdl_enabled() {
+    static const int on = [] {
+        const char* e = getenv("PINNJET_PDL");
+        return (e && e[0] == '1') ? 1 : 0;
+    }();
+    return on != 0;
+}
+
+// kern<<<grid, block, smem, s>>>(args...), optionally as a programmatic dependent of the kernel launched before it on `s`
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool dependent,
+                                 Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (dependent && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // CTA shape: NTC compute threads (128 or 256: template parameter of the kernels) + one producer warp.  Narrow networks
 // (hidden width <= 64) use 128-thread CTAs so that several CTAs share an SM and their GEMM / activation / program phases
@@ -95,6 +125,8 @@ struct K1Args {
     float* wts;
     float* loss_part;
     float* dbg;                          // diagnostic builds only (PJ_TIMING): phase cycle counters
+    float* sumsq_out;                    // non-null: the LAST warp to deliver its partial folds them all into *sumsq_out (+=)
+    unsigned* ticket;                    // ... found by this counter (zero between launches; lives in the loss-partial block)
 };
 
 struct K2Args {
@@ -118,6 +150,56 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// Programmatic dependent launch (K0 -> K1 -> finalize -> K2 -> K2b are launched with programmatic stream serialization, see
+// launch_kernel below): a kernel lets its successor's CTAs become resident right away (they take the SMs as this grid's
+// CTAs retire), and the successor blocks in pdl_wait() -- until this grid has COMPLETED and its memory is visible -- before it
+// touches anything this grid writes.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Loss finalisation inside the forward kernel (was a launch of its own): a program warp has stored its partial sum of
+// squared residuals; the warp that draws the last ticket adds ALL partials in the fixed order of the former
+// loss_finalize_kernel (lane-strided, then an xor-shuffle tree: run-to-run reproducible, identical numbers) to *sumsq_out and
+// re-arms the counter.  Called by whole warps; `lane0_stored` = lane 0 has written part[my index].
+__device__ __forceinline__ void fold_loss_partials(const float* part, unsigned n_parts, float* sumsq_out, unsigned* ticket, int lane) {
+    if (sumsq_out == nullptr) return;
+    unsigned last = 0;
+    if (lane == 0) {
+        __threadfence();                                   // my partial is visible before my ticket
+        last = atomicAdd(ticket, 1u) == n_parts - 1u ? 1u : 0u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    float s = 0.0f;
+    for (unsigned p = lane; p < n_parts; p += 32) s += __ldcg(part + p);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        *sumsq_out += s;
+        *ticket = 0u;
+    }
+}
+
+// K2b arithmetic, shared by k2_reduce_kernel and the fused reduce + all-reduce kernel (pinnjet_comm.cu) so that both give the
+// same bits: parameter i, partial group g of RED_GROUPS (contiguous ranges of the per-CTA partials, two accumulators each),
+// combined as ((g0+g1)+(g2+g3)) + ((g4+g5)+(g6+g7)).  A block handles RED_PARAMS parameters with one warp per group.
+constexpr int RED_PARAMS = 32, RED_GROUPS = 8;
+__device__ __forceinline__ float red_group_sum(const float* __restrict__ gpart, int n_parts, long long n_theta, long long i, int g) {
+    const int per = (n_parts + RED_GROUPS - 1) / RED_GROUPS, p_lo = g * per, p_hi = min(n_parts, p_lo + per);
+    float s0 = 0.0f, s1 = 0.0f;
+    int p = p_lo;
+    for (; p + 1 < p_hi; p += 2) {
+        s0 += gpart[(size_t)p * n_theta + i];
+        s1 += gpart[(size_t)(p + 1) * n_theta + i];
+    }
+    if (p < p_hi) s0 += gpart[(size_t)p * n_theta + i];
+    return s0 + s1;
+}
+__device__ __forceinline__ float red_combine(const float (*red)[RED_PARAMS], int il) {
+    return ((red[0][il] + red[1][il]) + (red[2][il] + red[3][il])) + ((red[4][il] + red[5][il]) + (red[6][il] + red[7][il]));
+}
+
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

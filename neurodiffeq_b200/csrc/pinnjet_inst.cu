@@ -16,32 +16,24 @@ namespace pj {
 
 #if PJ_N1 < 0
 
-// K2b: grad_theta[i] += sum over CTAs of partial[cta][i].  Block = 64 parameters x 4 groups of partials; fixed summation
-// order -> run-to-run reproducible.
-__global__ void k2_reduce_kernel(const float* __restrict__ gpart, int n_parts, long long n_theta,
-                                 float* __restrict__ grad) {
-    __shared__ float red[4][64];
-    const int il = threadIdx.x & 63, g = threadIdx.x >> 6;
-    const long long i = (long long)blockIdx.x * 64 + il;
-    float s = 0.0f;
-    if (i < n_theta) {
-        const int per = (n_parts + 3) / 4, p_lo = g * per, p_hi = min(n_parts, p_lo + per);
-        float s0 = 0.0f, s1 = 0.0f;
-        int p = p_lo;
-        for (; p + 1 < p_hi; p += 2) {
-            s0 += gpart[(size_t)p * n_theta + i];
-            s1 += gpart[(size_t)(p + 1) * n_theta + i];
-        }
-        if (p < p_hi) s0 += gpart[(size_t)p * n_theta + i];
-        s = s0 + s1;
-    }
-    red[g][il] = s;
+// K2b: grad_theta[i] += sum over CTAs of partial[cta][i].  Block = 32 parameters x 8 groups of partials (one warp per group:
+// coalesced 128-byte rows, ~19 dependent adds per thread for 148 partials); fixed summation order -> run-to-run reproducible.
+__global__ void __launch_bounds__(RED_PARAMS * RED_GROUPS) k2_reduce_kernel(const float* __restrict__ gpart, int n_parts, long long n_theta,
+                                                                             float* __restrict__ grad) {
+    __shared__ float red[RED_GROUPS][RED_PARAMS];
+    pdl_launch_dependents();
+    pdl_wait();                               // the reverse kernel's partials
+    const int il = threadIdx.x & (RED_PARAMS - 1), g = threadIdx.x / RED_PARAMS;
+    const long long i = (long long)blockIdx.x * RED_PARAMS + il;
+    red[g][il] = i < n_theta ? red_group_sum(gpart, n_parts, n_theta, i, g) : 0.0f;
     __syncthreads();
-    if (g == 0 && i < n_theta) grad[i] += (red[0][il] + red[1][il]) + (red[2][il] + red[3][il]);
+    if (g == 0 && i < n_theta) grad[i] += red_combine(red, il);
 }
 
 // sum of the per-CTA sums of squared residuals (fixed order) -> *out += total
 __global__ void loss_finalize_kernel(const float* __restrict__ part, int n_parts, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();                               // the forward kernel's per-CTA sums
     float s = 0.0f;
     for (int p = threadIdx.x; p < n_parts; p += 32) s += part[p];
 #pragma unroll
@@ -67,12 +59,11 @@ cudaError_t launch_tc_relayout(const K1Args& a, cudaStream_t s) {
 }
 
 cudaError_t launch_reduce(const float* gpart, int n_parts, long long n_theta, float* grad, cudaStream_t s) {
-    k2_reduce_kernel<<<(unsigned)((n_theta + 63) / 64), 256, 0, s>>>(gpart, n_parts, n_theta, grad);
-    return cudaGetLastError();
+    return launch_kernel(k2_reduce_kernel, dim3((unsigned)((n_theta + RED_PARAMS - 1) / RED_PARAMS)), dim3(RED_PARAMS * RED_GROUPS), 0, s, true,
+                         gpart, n_parts, n_theta, grad);
 }
 cudaError_t launch_loss_finalize(const float* part, int n_parts, float* out, cudaStream_t s) {
-    loss_finalize_kernel<<<1, 32, 0, s>>>(part, n_parts, out);
-    return cudaGetLastError();
+    return launch_kernel(loss_finalize_kernel, dim3(1), dim3(32), 0, s, true, part, n_parts, out);
 }
 
 #else
@@ -97,18 +88,17 @@ cudaError_t PJ_NAME(launch_k1_, PJ_N1, PJ_N2)(const K1Args& a, int grid, int sme
     if (a.plan.ntc1 == 128) {
         auto kern = k1_forward_kernel<128, kMinB1_128, kP1, 4, PJ_N1, PJ_N2, PJ_WL>;
         if (cudaError_t e = configure(kern, c128)) return e;
-        kern<<<grid, 160, smem, s>>>(a);
+        return launch_kernel(kern, dim3(grid), dim3(160), smem, s, true, a);
     } else if (a.plan.Q1 == 8) {
         auto kern = k1_forward_kernel<256, 1, kP1, kQ1, PJ_N1, PJ_N2, PJ_WL>;
         if (cudaError_t e = configure(kern, c256)) return e;
-        kern<<<grid, 320, smem, s>>>(a);
+        return launch_kernel(kern, dim3(grid), dim3(320), smem, s, true, a);
     } else {
         static int c256q4 = 0;
         auto kern = k1_forward_kernel<256, 1, kP1, 4, PJ_N1, PJ_N2, PJ_WL>;
         if (cudaError_t e = configure(kern, c256q4)) return e;
-        kern<<<grid, 320, smem, s>>>(a);
+        return launch_kernel(kern, dim3(grid), dim3(320), smem, s, true, a);
     }
-    return cudaGetLastError();
 }
 
 cudaError_t PJ_NAME(launch_k2_, PJ_N1, PJ_N2)(const K2Args& a, int grid, int smem, cudaStream_t s) {
@@ -116,20 +106,18 @@ cudaError_t PJ_NAME(launch_k2_, PJ_N1, PJ_N2)(const K2Args& a, int grid, int sme
         static int ctc = 0;
         auto kern = k2tc2_backward_kernel<PJ_N1, PJ_N2, PJ_WL>;
         if (cudaError_t e = configure(kern, ctc)) return e;
-        kern<<<grid, K2T_THREADS, smem, s>>>(a);
-        return cudaGetLastError();
+        return launch_kernel(kern, dim3(grid), dim3(K2T_THREADS), smem, s, true, a);
     }
     static int c128 = 0, c256 = 0;
     if (a.plan.ntc == 128) {
         auto kern = k2_backward_kernel<128, kMinB2_128, kP, kQ, PJ_N1, PJ_N2, PJ_WL>;
         if (cudaError_t e = configure(kern, c128)) return e;
-        kern<<<grid, 160, smem, s>>>(a);
+        return launch_kernel(kern, dim3(grid), dim3(160), smem, s, true, a);
     } else {
         auto kern = k2_backward_kernel<256, 1, kP, kQ, PJ_N1, PJ_N2, PJ_WL>;
         if (cudaError_t e = configure(kern, c256)) return e;
-        kern<<<grid, 288, smem, s>>>(a);
+        return launch_kernel(kern, dim3(grid), dim3(288), smem, s, true, a);
     }
-    return cudaGetLastError();
 }
 
 // tensor-core forward kernel (64-wide hidden layers); without the tensor-core reverse kernel the records are copied into
@@ -138,8 +126,7 @@ cudaError_t PJ_NAME(launch_k1tc_, PJ_N1, PJ_N2)(const K1Args& a, int grid, int s
     static int c = 0;
     auto kern = k1tc3_forward_kernel<PJ_N1, PJ_N2, PJ_WL>;
     if (cudaError_t e = configure(kern, c)) return e;
-    kern<<<grid, K1T_THREADS, smem, s>>>(a);
-    if (cudaError_t e = cudaGetLastError()) return e;
+    if (cudaError_t e = launch_kernel(kern, dim3(grid), dim3(K1T_THREADS), smem, s, true, a)) return e;
     if (a.mode == 1 && !a.plan.tc_bwd) {
         int n_hidden = 0;
         for (int n = 0; n < a.spec.n_nets; ++n) n_hidden += a.spec.net[n].n_linear - 1;

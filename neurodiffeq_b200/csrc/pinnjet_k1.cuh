@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(NTC + (NTC == 128 ? 32 : 64), MINB) k1_forward
         }
         fence_barrier_init();
     }
+    pdl_launch_dependents();
+    pdl_wait();                       // K0 (pack) has completed: theta_pack is readable
     for (int i = tid; i < pl.small_floats; i += NT_TOTAL) small[i] = __ldg(A.pack + i);
     for (int i = tid; i < A.prog_len; i += NT_TOTAL) prog_s[i] = __ldg(A.prog + i);
     if constexpr (WL > 0)
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(NTC + (NTC == 128 ? 32 : 64), MINB) k1_forward
         }
         my_sumsq = warp_sum(my_sumsq);
         if (lane == 0) A.loss_part[blockIdx.x] = my_sumsq;
+        fold_loss_partials(A.loss_part, gridDim.x, A.sumsq_out, A.ticket, lane);
         return;
     }
 

@@ -80,6 +80,7 @@ __device__ __forceinline__ void k1tc3_body(const K1Args& A) {
     const int sT = pl.seed_T;                                        // tile size of the seed / weight layouts K2 reads
     const long long ws_points = (long long)pl.n_tiles * pl.T;
 
+    pdl_launch_dependents();
     if (tid == 0) {
 #ifdef PJ_TIMING
         *reinterpret_cast<unsigned long long*>(tmem_slot + 2) = clock64();
@@ -117,6 +118,8 @@ __device__ __forceinline__ void k1tc3_body(const K1Args& A) {
     if (warp == TC_NCW) {   // ================= TMA + MMA warp =================
         TC_TRACE(tr, A.dbg, 200, 100, t0_, blockIdx.x == 0 && lane == 0)
         if (lane == 0) {
+            pdl_wait();   // K0 (pack) has completed.  Only this thread reads theta_pack (bulk TMA); every other warp gets the
+                          // weights through shared memory + mbarriers, so barriers / TMEM / the coordinate prefetch start early
             const uint32_t small_bytes = (uint32_t)((pl.small_floats * 4 + 15) / 16 * 16);
             const uint32_t prog_bytes = (uint32_t)A.prog_len * 16u, progw_bytes = WL > 0 ? (uint32_t)A.prog_w_len * 16u : 0u;
             const uint32_t w_bytes = (uint32_t)n_hh * 3u * TC_WIMG + (uint32_t)sp.n_nets * 3u * TC_WOUT;
@@ -176,7 +179,7 @@ __device__ __forceinline__ void k1tc3_body(const K1Args& A) {
     }
 
     if (warp == TC_NCW + 1 + K1T_NPW) {   // ================= prefetch warp: coordinates and weights of the tiles ahead =====
-        if constexpr (WL > 0) mbar_wait(wfull, 0);   // the weight program
+        if constexpr (WL > 0 && !JIT) mbar_wait(wfull, 0);   // the weight program (interpreted: it lives in shared memory)
         const int NW = sp.n_nets * WL;
 #pragma unroll 1
         for (int iter = 0; iter < my_tiles; ++iter) {
@@ -202,12 +205,16 @@ __device__ __forceinline__ void k1tc3_body(const K1Args& A) {
                     }
                 }
                 __syncwarp();
-                if (train)   // K2 needs the same weights: workspace [tile of sT points][NW][sT]
+                if (train) {   // K2 needs the same weights: workspace [tile of sT points][NW][sT]
+                    // the only global store of this kernel that is not behind the weights' mbarrier: with batches back to
+                    // back (no K0 in between) the previous reverse kernel may still be reading this area
+                    if (iter == 0) pdl_wait();
                     for (int e = lane; e < NW * TP; e += 32) {
                         const int wr = e / TP, wp = e - wr * TP;
                         const long long g2 = base + wp;
                         if (g2 < ws_points) A.wts[(g2 / sT) * ((long long)NW * sT) + (long long)wr * sT + (g2 % sT)] = wb[e];
                     }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&pre_full[rb]);
@@ -256,6 +263,7 @@ __device__ __forceinline__ void k1tc3_body(const K1Args& A) {
         }
         my_sumsq = warp_sum(my_sumsq);
         if (lane == 0) A.loss_part[K1T_NPW * blockIdx.x + pw] = my_sumsq;
+        fold_loss_partials(A.loss_part, K1T_NPW * gridDim.x, A.sumsq_out, A.ticket, lane);
         return;
     }
 

@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(NTC + 32, MINB) k2_backward_kernel(const __gri
         mbar_init(zfull, 1);
         fence_barrier_init();
     }
+    pdl_launch_dependents();
+    pdl_wait();                       // the forward kernel (records, seeds) and, before it, K0 have completed
     for (int i = tid; i < pl.small_floats; i += NT_TOTAL) small[i] = __ldg(A.pack + i);
     for (int i = tid; i < pl.sgrad_floats * pl.sgrad_copies; i += NT_TOTAL) sgrad[i] = 0.0f;
     for (long long i = tid; i < sp.n_theta; i += NT_TOTAL) gpart[i] = 0.0f;

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
     for (int n = 0; n < sp.n_nets; ++n) n_hh += sp.net[n].n_linear - 2;
     const int tmem_cols = 64 * (1 + n_hh) <= 128 ? 128 : (64 * (1 + n_hh) <= 256 ? 256 : 512);
 
+    pdl_launch_dependents();
     if (tid == 0) {
 #ifdef PJ_TIMING
         *reinterpret_cast<unsigned long long*>(tmem_slot + 2) = clock64();
@@ -119,14 +120,18 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2tc2_backward_kernel(const __
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    for (int i = tid; i < 4 * pl.sgrad_floats; i += K2T_THREADS) sgrad[i] = 0.0f;
+    if constexpr (G::CP != C)   // rows of padded channels are never written: they must read as zero in both GEMMs
+        for (int i = tid; i < 2 * 3 * TC_AIMG / 16; i += K2T_THREADS) reinterpret_cast<uint4*>(zimg)[i] = make_uint4(0, 0, 0, 0);
+    // everything above is CTA-local and runs while the forward kernel drains; from here on global memory is touched: the
+    // forward kernel (records, seeds), K0 before it and -- with batches back to back -- the previous K2b (reads the gradient
+    // partials zeroed below) must have completed
+    pdl_wait();
     for (int i = tid; i < sp.n_nets * PJ_MAX_NETS * TC_H; i += K2T_THREADS) {
         const int n = i / (PJ_MAX_NETS * TC_H), r = i - n * (PJ_MAX_NETS * TC_H);
         wlo_s[i] = r < sp.net[n].width[sp.net[n].n_linear] * TC_H ? __ldg(A.pack + pl.s_wlo[n] + r) : 0.0f;
     }
-    for (int i = tid; i < 4 * pl.sgrad_floats; i += K2T_THREADS) sgrad[i] = 0.0f;
     for (long long i = tid; i < sp.n_theta; i += K2T_THREADS) gpart[i] = 0.0f;   // parameters no network of the spec owns
-    if constexpr (G::CP != C)   // rows of padded channels are never written: they must read as zero in both GEMMs
-        for (int i = tid; i < 2 * 3 * TC_AIMG / 16; i += K2T_THREADS) reinterpret_cast<uint4*>(zimg)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();

@@ -99,8 +99,10 @@ class EagerProblem:
                         self.grad[off:off + n].zero_()
                     p.grad = self.grad[off:off + n].view(p.shape)
 
-    def pack(self):
+    def pack(self, zero_gradbuf=False):
         """Nothing to re-layout: autograd reads the live parameters."""
+        if zero_gradbuf:
+            self.gradbuf.zero_()
 
     def enable_jit(self, strict=False):
         if strict:
@@ -150,7 +152,9 @@ class EagerProblem:
         return u, (r if want_residual else None), (self.sumsq if want_sumsq else None)
 
     def residual_grad(self, coords, n_global=None, want_residual=False, rbar=None, sumsq_out=None, repack=True, ubar=None,
-                      reducer=None):
+                      reducer=None, zero_gradbuf=False):
+        if zero_gradbuf:
+            self.gradbuf.zero_()
         n = coords[0].numel()
         n_glob = n if n_global is None else n_global
         funcs, res, aux = self._evaluate(coords)

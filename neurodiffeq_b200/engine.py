@@ -70,6 +70,8 @@ def load_library():
     lib.pj_plan_info.argtypes = [ctypes.POINTER(PjSpec), i64, ctypes.POINTER(i64), i32]
     lib.pj_plan_info.restype = ctypes.c_int
     lib.pj_pack.argtypes = [ctypes.POINTER(PjSpec), vp, vp, vp]
+    lib.pj_pack_zero.argtypes = [ctypes.POINTER(PjSpec), vp, vp, vp, i64, vp]
+    lib.pj_pack_zero.restype = ctypes.c_int
     lib.pj_forward.argtypes = [ctypes.POINTER(PjSpec), vp, i32, vp, i32, ctypes.POINTER(vp), i64, vp, vp, vp, vp, vp,
                                ctypes.c_size_t, vp]
     lib.pj_forward_train.argtypes = [ctypes.POINTER(PjSpec), vp, i32, vp, i32, ctypes.POINTER(vp), i64, vp, f32, vp, vp,
@@ -93,7 +95,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ("pj_abi_version", "pj_last_error", "pj_sizes", "pj_plan_info", "pj_pack", "pj_forward", "pj_forward_train",
                     "pj_backward", "pj_allreduce_bytes", "pj_allreduce_oneshot", "pj_sample", "pj_adam_step", "pj_forward_jit",
-                    "pj_forward_train_jit", "pj_backward_allreduce_bytes", "pj_backward_allreduce")
+                    "pj_forward_train_jit", "pj_backward_allreduce_bytes", "pj_backward_allreduce", "pj_pack_zero")
 
 
 def _check(rc, what):
@@ -355,6 +357,7 @@ class FusedProblem:
         need = sz.workspace_bytes if train else 4096
         if self.workspace is None or self.workspace.numel() < need:
             self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self.workspace[:4096].zero_()   # loss partials + the ticket of the in-kernel loss finalisation start at zero
             self._graphs.clear()          # captured graphs hold the old workspace pointer
         return sz
 
@@ -388,11 +391,17 @@ class FusedProblem:
         return (self.prog_w.data_ptr(), len(self.tp.prog_w)) if self.tp.wl else (None, 0)
 
     # ---- kernels ------------------------------------------------------------------------------------------------------
-    def pack(self):
-        """K0: re-layout theta for the kernels.  Must run after every change of the parameters (optimizer step)."""
+    def pack(self, zero_gradbuf=False):
+        """K0: re-layout theta for the kernels.  Must run after every change of the parameters (optimizer step).
+        ``zero_gradbuf=True`` clears ``gradbuf`` = [grad | sum r^2] in the same launch (``optimizer.zero_grad()`` + the loss
+        accumulator of the step, without a fill launch)."""
         self._ensure_buffers(1, False)
-        _check(self.lib.pj_pack(ctypes.byref(self.spec), self.theta.data_ptr(), self.pack_buf.data_ptr(),
-                                self._stream()), "pj_pack")
+        if zero_gradbuf:
+            _check(self.lib.pj_pack_zero(ctypes.byref(self.spec), self.theta.data_ptr(), self.pack_buf.data_ptr(),
+                                         self.gradbuf.data_ptr(), self.gradbuf.numel(), self._stream()), "pj_pack_zero")
+        else:
+            _check(self.lib.pj_pack(ctypes.byref(self.spec), self.theta.data_ptr(), self.pack_buf.data_ptr(),
+                                    self._stream()), "pj_pack")
         if self._patch_sets:
             self._apply_patches()
         self.kernel_launches += 1
@@ -420,19 +429,23 @@ class FusedProblem:
         return u, r, (self.sumsq if want_sumsq else None)
 
     def residual_grad(self, coords, n_global=None, want_residual=False, rbar=None, sumsq_out=None, repack=True, ubar=None,
-                      reducer=None):
+                      reducer=None, zero_gradbuf=False):
         """K1(train)+K2+K2b: ``grad`` += d/dtheta mean(r^2) (or of the caller's loss when ``rbar`` = dL/dr [n_eq, N] and,
         for losses that also depend on the functions, ``ubar`` = dL/du [n_funcs, N] are given);
         returns (sum r^2 device tensor, residual or None).  mean(r^2) = sumsq / (N_global * n_eq).
         ``reducer`` (a ``parallel.GradBufReducer`` built for ``self.gradbuf``): afterwards ``gradbuf`` = [grad | sum r^2]
         holds the SUM over the ranks -- K2b and the collective as one kernel when the reducer offers it
-        (``pj_backward_allreduce``), K2b followed by the reducer otherwise."""
+        (``pj_backward_allreduce``), K2b followed by the reducer otherwise.
+        ``zero_gradbuf=True`` (needs ``repack=True`` and ``sumsq_out=self.sumsq``): K0 clears ``gradbuf`` first, i.e. the call
+        computes the gradient of THIS batch instead of accumulating."""
         n = coords[0].numel()
         if ubar is not None:
             self.enable_function_adjoints()      # may enlarge spec.n_slots: before any size / plan query
         self._ensure_buffers(n, True)
+        if zero_gradbuf and (not repack or sumsq_out is not self.sumsq):
+            raise ValueError("zero_gradbuf=True needs repack=True and sumsq_out=self.sumsq")
         if repack:
-            self.pack()
+            self.pack(zero_gradbuf=zero_gradbuf)
         ptrs, keep = self._coord_ptrs(coords, n)
         n_glob = n if n_global is None else n_global
         scale = 2.0 / (float(n_glob) * self.n_eq)

@@ -431,9 +431,9 @@ class BaseSolver:
         metric_values = {name: 0.0 for name in self.metrics_fn}
         n_b = self.n_batches[key]
         loss_acc = torch.zeros(1, dtype=torch.float32, device=self.device)
-        if key == "train":
-            fp.gradbuf.zero_()          # optimizer.zero_grad(): the kernels accumulate into p.grad views
-        fp.pack()                       # parameters changed at the last optimizer step
+        # parameters changed at the last optimizer step: K0 re-packs them and, for a training phase, clears [grad | sum r^2]
+        # in the same launch (optimizer.zero_grad(): the kernels accumulate into the p.grad views)
+        fp.pack(zero_gradbuf=(key == "train"))
         for _ in range(n_b):
             coords = self._generate_batch(key)
             denom = float(self._n_global * fp.n_eq)          # loss of a batch = mean over its N_global * n_eq entries
@@ -573,9 +573,9 @@ class BaseSolver:
         def body():
             lo, hi, n_glob = st.bounds["train"]
             st.samplers["train"].sample_into(st.coords["train"], lo, hi - lo)
-            fp.gradbuf.zero_()
-            # K0, K1, finalize, K2, K2b; under data parallelism K2b and the collective are one kernel (pj_backward_allreduce)
-            fp.residual_grad(st.coords["train"], n_global=n_glob, sumsq_out=fp.sumsq, reducer=st.reducer)
+            # K0 (pack + clear [grad | sum r^2]), K1 (+ loss finalisation), K2, K2b; under data parallelism K2b and the
+            # collective are one kernel (pj_backward_allreduce)
+            fp.residual_grad(st.coords["train"], n_global=n_glob, sumsq_out=fp.sumsq, reducer=st.reducer, zero_gradbuf=True)
             train_loss = fp.sumsq / float(n_glob * fp.n_eq)
             if n_valid == 0:   # lowest loss / best parameters from the training loss, before the optimizer step (reference
                 opt._step_fused(train_loss, st.best_loss, st.best_theta)       # solvers.py:411-412), in the Adam launch

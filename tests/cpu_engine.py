@@ -46,8 +46,9 @@ class CpuFusedProblem:
     def relink(self):
         pass
 
-    def pack(self):
-        pass
+    def pack(self, zero_gradbuf=False):
+        if zero_gradbuf:
+            self.gradbuf.zero_()
 
     def _per_instance(self):
         by_param = {id(p): p.detach().numpy() for p in self.params}

@@ -12,6 +12,13 @@ from test_losses_gpu import oracle_training_with_loss
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def fresh_warning_registry(monkeypatch):
+    """the fallback warns ONCE per reason and process: every test starts with a clean slate"""
+    import neurodiffeq_b200.eager as E
+    monkeypatch.setattr(E, "_WARNED", set())
+
+
 @pytest.mark.parametrize("key", workloads.FALLBACK_NAMES)
 def test_refused_problem_trains_on_the_autograd_path_gpu(key):
     n, epochs = 500, 5

@@ -85,3 +85,39 @@ def test_library_is_the_path():
     assert os.path.exists(engine.library_path())
     with open("/proc/self/maps") as f:
         assert "libpinnjet.so" in f.read()
+
+
+@pytest.mark.parametrize("key", ["c1", "c2", "c3"])
+def test_pack_clears_the_gradient_buffer_and_the_loss_is_finalised_in_kernel(key):
+    """K0 with zero_gradbuf (pj_pack_zero) packs like pj_pack and clears [grad | sum r^2]; the forward kernel's last warp
+    folds the per-CTA partial sums itself (ticket re-armed for the next launch): repeated launches give identical sums."""
+    wl, nets, conds, fp = build_fused(key, seed=3)
+    n = 5000
+    coords = [torch.from_numpy(c).cuda() for c in workloads.sample_coords(wl, n, seed=5)]
+    fp.pack()
+    torch.cuda.synchronize()
+    packed = fp.pack_buf.clone()
+    fp.gradbuf.fill_(7.0)
+    fp.pack_buf.zero_()                     # regions no kernel reads (padding, images of the other kernel family) stay zero
+    fp.pack(zero_gradbuf=True)
+    torch.cuda.synchronize()
+    assert torch.equal(fp.pack_buf, packed)
+    assert float(fp.gradbuf.abs().max()) == 0.0
+    sums = []
+    for _ in range(6):
+        _, r, s = fp.forward(coords, want_u=False, want_residual=True, want_sumsq=True)
+        sums.append(float(s.item()))
+    ref = float((r.double() ** 2).sum())
+    assert len(set(sums)) == 1 and abs(sums[0] - ref) <= 1e-5 * ref
+    fp.gradbuf.zero_()
+    fp.residual_grad(coords, sumsq_out=fp.sumsq)
+    torch.cuda.synchronize()
+    g1 = fp.gradbuf.clone()
+    for _ in range(3):      # clears the stale content, never accumulates
+        fp.gradbuf.fill_(3.0)
+        fp.residual_grad(coords, sumsq_out=fp.sumsq, zero_gradbuf=True)
+        torch.cuda.synchronize()
+        assert torch.equal(fp.gradbuf, g1)
+    fp.residual_grad(coords, sumsq_out=fp.sumsq)            # and without the flag it still accumulates
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(fp.gradbuf.cpu().numpy(), 2.0 * g1.cpu().numpy(), rtol=1e-6, atol=1e-7)
