@@ -425,7 +425,7 @@ class FusedProblem:
             _check(self.lib.pj_forward_jit(self._jit.function, *args), "pj_forward_jit")
         else:
             _check(self.lib.pj_forward(*args), "pj_forward")
-        self.kernel_launches += 2 if want_sumsq else 1
+        self.kernel_launches += 1          # the loss finalisation happens inside the forward kernel
         return u, r, (self.sumsq if want_sumsq else None)
 
     def residual_grad(self, coords, n_global=None, want_residual=False, rbar=None, sumsq_out=None, repack=True, ubar=None,
@@ -495,7 +495,7 @@ class FusedProblem:
                                         self.workspace.data_ptr(), self.workspace.numel(), self._stream()), "pj_backward")
             if reducer is not None:
                 reducer(self.gradbuf)
-        self.kernel_launches += 4
+        self.kernel_launches += 3          # K1 (+ loss finalisation), K2, K2b (or K2b + collective as one kernel)
         return sumsq_out, r
 
     # ---- specialised forward kernel (jit.py): the programs compiled into the kernel instead of interpreted ---------------
@@ -627,7 +627,7 @@ class FusedProblem:
         graph, static, stage = st
         self._stage_coords(static, stage, coords)
         graph.replay()
-        self.kernel_launches += 5 if train else 3
+        self.kernel_launches += 4 if train else 2
         return self.sumsq
 
     def train_step_graphed(self, coords, optimizer, n_global=None):
