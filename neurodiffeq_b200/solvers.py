@@ -118,7 +118,7 @@ class BaseSolver:
     def __init__(self, diff_eqs, conditions, nets=None, train_generator=None, valid_generator=None,
                  analytic_solutions=None, optimizer=None, loss_fn=None, n_batches_train=1, n_batches_valid=4,
                  metrics=None, n_input_units=None, n_output_units=None, shuffle=None, batch_size=None,
-                 device=None, data_parallel=True, device_loop=False, jit=False):
+                 device=None, data_parallel=True, device_loop=False, jit=None):
         if shuffle:
             warnings.warn("param `shuffle` is deprecated and ignored; shuffling should be performed by generators",
                           FutureWarning)
@@ -178,7 +178,11 @@ class BaseSolver:
                                          enforce=self.compute_func_val)
             self.n_eq = self.problem.n_eq - (n_coords if self._h1 else 0)     # the user's equations
         self.device = self.problem.device
-        if jit or os.environ.get("PINNJET_JIT") == "1":   # opt-in: the residual programs compiled into the forward kernel
+        # The residual programs compiled INTO the forward kernel (jit.py: ~1 s of nvcc per problem, cached on disk; identical
+        # numbers).  Default (jit=None): on whenever it applies -- tensor-core path, a compiler on the machine -- and silently
+        # the in-kernel interpreter otherwise (problem.jit_reason says why); jit=False or PINNJET_JIT=0 keep the interpreter.
+        env = os.environ.get("PINNJET_JIT")
+        if jit or (jit is None and env != "0") or (jit is not False and env == "1"):
             self.problem.enable_jit()
 
         self.optimizer = optimizer if optimizer else torch.optim.Adam(

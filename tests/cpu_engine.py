@@ -46,6 +46,11 @@ class CpuFusedProblem:
     def relink(self):
         pass
 
+    jit_reason = "CPU stand-in"
+
+    def enable_jit(self, strict=False):
+        return False
+
     def pack(self, zero_gradbuf=False):
         if zero_gradbuf:
             self.gradbuf.zero_()
