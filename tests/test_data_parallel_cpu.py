@@ -94,6 +94,8 @@ def _solver_worker(rank, world, port, key, out_dir, loss_fn=None):
     kw = {} if loss_fn is None else dict(loss_fn=loss_fn)
     if key == "c2":
         kw["metrics"] = {"mean_u": _mean_u}
+    if key.startswith("y"):        # refused by the tracer: the autograd fallback (eager.py), here on CPU tensors
+        kw["device"] = "cpu"
     n_pts = 151 if key == "x4" or kw.get("loss_fn") == "l1" else 150      # odd: the two ranks get 76 / 75 points
     wl, solver, nets, coords_np = make_solver(key, n_pts, **kw)  # same seed on every rank -> same parameters, same batch
     assert solver._dist is not None
@@ -106,7 +108,7 @@ def _solver_worker(rank, world, port, key, out_dir, loss_fn=None):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("key,loss_fn", [("c2", None), ("x4", None), ("c2", "l1"), ("c2", _funcs_loss)])
+@pytest.mark.parametrize("key,loss_fn", [("c2", None), ("x4", None), ("c2", "l1"), ("c2", _funcs_loss), ("y1", None)])
 def test_solver_fit_on_two_ranks_equals_one_process(key, loss_fn, tmp_path, monkeypatch):
     """Solver.fit under torch.distributed: every rank samples the same batch, keeps its slice, the flat
     [grad | sum r^2] buffer is all-reduced once per epoch phase and the replicated Adam stays in lock-step -- losses and
@@ -128,7 +130,8 @@ def test_solver_fit_on_two_ranks_equals_one_process(key, loss_fn, tmp_path, monk
     torch.set_default_dtype(torch.float64)
     try:
         n_pts = 151 if key == "x4" or loss_fn == "l1" else 150
-        wl, solver, nets, _ = make_solver(key, n_pts, **({} if loss_fn is None else dict(loss_fn=loss_fn)))
+        extra = dict(device="cpu") if key.startswith("y") else {}
+        wl, solver, nets, _ = make_solver(key, n_pts, **({} if loss_fn is None else dict(loss_fn=loss_fn)), **extra)
         solver.fit(3, tqdm_file=None)
     finally:
         torch.set_default_dtype(old)
