@@ -484,6 +484,8 @@ class FusedProblem:
             self._accumulate_shortcut_grads(keep, n)
         if reducer is not None and sumsq_out is not self.sumsq:
             raise ValueError("residual_grad(reducer=...) sums self.gradbuf: pass sumsq_out=self.sumsq")
+        if reducer is not None and getattr(reducer, "n", self.gradbuf.numel()) != self.gradbuf.numel():
+            raise ValueError("residual_grad(reducer=...): the reducer was built for a buffer of another size than gradbuf")
         if reducer is not None and reducer.fused_args is not None:
             peers, rank, world = reducer.fused_args
             _check(self.lib.pj_backward_allreduce(ctypes.byref(self.spec), ptrs, n, self.pack_buf.data_ptr(),

@@ -40,7 +40,7 @@ class GradBufReducer:
 
     def __init__(self, buf, dist=None):
         dist = dist or torch.distributed
-        self.dist, self.mode, self.why, self.fused_args = dist, "single", "", None
+        self.dist, self.mode, self.why, self.fused_args, self.n = dist, "single", "", None, buf.numel()
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
             return
         self.mode = "process-group"
@@ -75,8 +75,6 @@ class GradBufReducer:
             self._rank, self._world, self._n, self._lib = dist.get_rank(), world, n, lib
             fused = None
             if os.environ.get("PINNJET_FUSED_AR", "1") != "0":   # every rank reads the same environment: same rendezvous count
-                from . import engine as _e
-                lib = _e.load_library()
                 words_f = int(lib.pj_backward_allreduce_bytes(n, world)) // 4
                 self._sym_f = symm.empty(words_f, dtype=torch.float32, device=buf.device)
                 self._sym_f.zero_()
