@@ -182,10 +182,10 @@ class EagerProblem:
             reducer(self.gradbuf)
         return sumsq_out, (r.detach().t().contiguous() if want_residual else None)
 
-    def residual_grad_graphed(self, coords, n_global=None, train=True):
+    def residual_grad_graphed(self, coords, n_global=None, train=True, zero_gradbuf=False):
         """Same contract as the fused engine's (``grad`` and ``sumsq`` ACCUMULATE); no graph: autograd re-traces every batch."""
         if train:
-            self.residual_grad(coords, n_global=n_global, sumsq_out=self.sumsq)
+            self.residual_grad(coords, n_global=n_global, sumsq_out=self.sumsq, zero_gradbuf=zero_gradbuf)
         else:
             _, r, _ = self.forward(coords, want_u=False, want_residual=True)
             with torch.no_grad():

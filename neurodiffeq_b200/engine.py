@@ -567,8 +567,8 @@ class FusedProblem:
         while len(self._graphs) > self.GRAPH_CACHE_SIZE:    # evict the least recently used graph and its static / pinned buffers
             self._graphs.pop(next(iter(self._graphs)))
 
-    def _graph_state(self, n, n_global, train):
-        key = (int(n), int(n_global), bool(train))
+    def _graph_state(self, n, n_global, train, zero_gradbuf=False):
+        key = (int(n), int(n_global), bool(train), bool(zero_gradbuf))
         st = self._graph_lookup(key)
         if st is not None:
             return st
@@ -580,7 +580,7 @@ class FusedProblem:
 
         def body():
             if train:
-                self.residual_grad(static, n_global=n_global, sumsq_out=self.sumsq)
+                self.residual_grad(static, n_global=n_global, sumsq_out=self.sumsq, zero_gradbuf=zero_gradbuf)
             else:
                 self.forward(static, want_u=False, want_residual=False, want_sumsq=True)
 
@@ -611,18 +611,20 @@ class FusedProblem:
             else:
                 stage.copy_in(i, dst, src)
 
-    def residual_grad_graphed(self, coords, n_global=None, train=True):
+    def residual_grad_graphed(self, coords, n_global=None, train=True, zero_gradbuf=False):
         """Same contract as :meth:`residual_grad` with ``sumsq_out=self.sumsq`` (``grad`` and ``sumsq`` ACCUMULATE; zero
-        ``gradbuf`` yourself), but K0+K1+finalize+K2+K2b are replayed from a CUDA graph captured once per batch size.
+        ``gradbuf`` yourself, or pass ``zero_gradbuf=True`` and K0 clears it inside the graph), but K0+K1+K2+K2b are
+        replayed from a CUDA graph captured once per batch size.
         ``coords`` may be host tensors (staged through persistent pinned buffers) or device tensors.
         ``train=False`` replays the validation path (sum of squared residuals only)."""
         n = coords[0].numel()
         n_glob = n if n_global is None else n_global
-        st = self._graph_state(n, n_glob, train)
+        zero_gradbuf = bool(zero_gradbuf and train)
+        st = self._graph_state(n, n_glob, train, zero_gradbuf)
         if st is None:                                  # graph cache exhausted (see GRAPH_MAX_DISTINCT): eager launches
             dev_coords = [c.detach().reshape(-1).to(self.device, torch.float32) for c in coords]
             if train:
-                self.residual_grad(dev_coords, n_global=n_glob, sumsq_out=self.sumsq)
+                self.residual_grad(dev_coords, n_global=n_glob, sumsq_out=self.sumsq, zero_gradbuf=zero_gradbuf)
             else:
                 self.forward(dev_coords, want_u=False, want_residual=False, want_sumsq=True)   # like the graphed body
             return self.sumsq

@@ -87,7 +87,9 @@ class CpuFusedProblem:
     def grads_as_list(self):
         return [self.grad[o:o + p.numel()].view(p.shape).detach().numpy().copy() for p, o in zip(self.params, self.offsets)]
 
-    def residual_grad_graphed(self, coords, n_global=None, train=True):
+    def residual_grad_graphed(self, coords, n_global=None, train=True, zero_gradbuf=False):
+        if zero_gradbuf and train:
+            self.gradbuf.zero_()
         if train:
             self.residual_grad(coords, n_global=n_global, sumsq_out=self.sumsq)
         else:
