@@ -3,7 +3,7 @@
 Run in the build container only (``python tests/golden/generate.py``); the GPU box has no /root/reference, so the
 ``.npz`` files written next to this script are committed and are what the tests read.
 
-For every workload of workloads.py (BASELINE.json's C1..C5 and the extension cases x1..) at N points the script evaluates exactly the closure of
+For every workload of workloads.py (BASELINE.json's C1..C5, the extension cases x1.. and the fallback cases y1..) at N points the script evaluates exactly the closure of
 the reference (solvers.py:369-395): ``funcs = cond.enforce(net, *coords)``; ``r = cat(diff_eqs(*funcs, *coords))``;
 ``loss = (r**2).mean()``; ``loss.backward()`` -- in float64 (the reference's import default) on inputs whose
 values are float32-representable (so that the fp64 result is "the exact answer" for the fp32 inputs the CUDA path
@@ -28,7 +28,7 @@ import ref_shim  # noqa: E402
 import workloads  # noqa: E402
 
 GOLDEN_N = {"c1": 256, "c2": 256, "c3": 256, "c4": 256, "c5": 256, "x1": 256, "x2": 256, "x3": 256, "x4": 256, "x5": 256,
-            "x6": 256, "x7": 256, "x8": 256, "x9": 256}
+            "x6": 256, "x7": 256, "x8": 256, "x9": 256, "y1": 256, "y2": 256}
 
 
 def reference_namespace():
@@ -73,7 +73,7 @@ def run_closure(wl, nets, conds, coords_np, dtype):
 def main():
     nd = reference_namespace()
     only = sys.argv[1:]   # e.g. `generate.py x1 x2`: (re)generate just these; default: every workload
-    for key in workloads.NAMES + workloads.EXTRA_NAMES:
+    for key in workloads.NAMES + workloads.EXTRA_NAMES + workloads.FALLBACK_NAMES:
         if only and key not in only:
             continue
         wl = workloads.build(nd, key)

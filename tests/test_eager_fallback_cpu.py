@@ -162,3 +162,30 @@ def test_live_solution_follows_training_on_the_autograd_path():
     assert float((u2 - u1).abs().max()) > 0
     solver.fit(1, tqdm_file=None)               # the solver re-adopts its parameters after the solution borrowed them
     assert np.isfinite(solver.metrics_history["train_loss"][-1])
+
+
+@pytest.mark.parametrize("key", workloads.FALLBACK_NAMES)
+def test_autograd_path_matches_reference_golden(key):
+    """The fallback engine itself (forward / residual_grad through the FusedProblem interface) against golden vectors made by
+    the UNMODIFIED reference (tests/golden/generate.py) -- the same check the fused kernels get for C1..C5 / x1..x9."""
+    from conftest import load_golden
+    from neurodiffeq_b200.eager import EagerProblem
+    wl = workloads.build(workloads.product_namespace(), key)
+    gold = load_golden(wl.name)
+    nets, conds = wl.make_nets(), wl.make_conditions()
+    workloads.set_params(nets, gold["params"])
+    ep = EagerProblem(nets, conds, wl.diff_eqs, len(wl.coord_names), device="cpu", reason="test")
+    coords = [torch.from_numpy(c.astype(np.float64)) for c in gold["coords"]]
+    u, r, s = ep.forward(coords, want_sumsq=True)
+    n = gold["coords"].shape[1]
+    np.testing.assert_allclose(u.numpy(), gold["u"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(r.numpy(), gold["residual"], rtol=1e-10, atol=1e-11)
+    assert abs(float(s) / (n * ep.n_eq) - gold["loss"]) <= 1e-12 * gold["loss"]
+    ep.gradbuf.zero_()
+    s2, r2 = ep.residual_grad(coords, want_residual=True)
+    assert abs(float(s2) / (n * ep.n_eq) - gold["loss"]) <= 1e-12 * gold["loss"]
+    for g, h in zip(ep.grads_as_list(), gold["grads"]):
+        np.testing.assert_allclose(g, h, rtol=1e-9, atol=1e-11 * max(1.0, np.abs(h).max()))
+    ep.residual_grad(coords)                      # accumulates like loss.backward()
+    for g, h in zip(ep.grads_as_list(), gold["grads"]):
+        np.testing.assert_allclose(g, 2.0 * h, rtol=1e-9, atol=1e-11 * max(1.0, np.abs(h).max()))

@@ -69,3 +69,4 @@ def test_live_solution_follows_training_gpu():
         assert float((a - c).abs().max()) > 0
     solver.fit(1, tqdm_file=None)
     assert np.isfinite(solver.metrics_history["train_loss"][-1])
+

@@ -8,7 +8,7 @@ from conftest import load_golden
 from oracle import reference_port as oracle
 
 
-@pytest.mark.parametrize("key", workloads.NAMES + workloads.EXTRA_NAMES)
+@pytest.mark.parametrize("key", workloads.NAMES + workloads.EXTRA_NAMES + workloads.FALLBACK_NAMES)
 def test_oracle_matches_reference_golden(key):
     wl = workloads.build(oracle.NAMESPACE, key)
     gold = load_golden(wl.name)
