@@ -28,7 +28,7 @@ import ref_shim  # noqa: E402
 import workloads  # noqa: E402
 
 GOLDEN_N = {"c1": 256, "c2": 256, "c3": 256, "c4": 256, "c5": 256, "x1": 256, "x2": 256, "x3": 256, "x4": 256, "x5": 256,
-            "x6": 256, "x7": 256, "x8": 256, "x9": 256, "y1": 256, "y2": 256}
+            "x6": 256, "x7": 256, "x8": 256, "x9": 256, "y1": 256, "y2": 256, "y3": 256}
 
 
 def reference_namespace():

@@ -40,17 +40,18 @@ def test_refused_problem_trains_on_the_autograd_path(key):
     for a, b in zip(get_params(nets), ref_params):
         np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
     # solutions and residuals come from the same path
-    t = torch.linspace(0.1, 1.9, 9)
-    u = solver.get_solution(best=False)(t)
-    r = solver.get_residuals(t, best=False)
+    pts = [torch.linspace(lo + 0.05 * (hi - lo), hi - 0.05 * (hi - lo), 9) * (1.0 + 0.01 * i)
+           for i, (lo, hi) in enumerate(wl.coord_ranges)]
+    u = solver.get_solution(best=False)(*pts)
+    r = solver.get_residuals(*pts, best=False)
     assert u.shape == (9,) and r.shape == (9,)
     from oracle import reference_port as oracle
     owl = workloads.build(oracle.NAMESPACE, key)
     onets, oconds = owl.make_nets(), owl.make_conditions()
     oracle.load_params(onets, get_params(nets), dtype=torch.float64)
-    tt = t.reshape(-1, 1).requires_grad_(True)
-    uo = oconds[0].enforce(onets[0], tt)
-    ro = owl.diff_eqs(uo, tt)[0]
+    cols = [p.reshape(-1, 1).requires_grad_(True) for p in pts]
+    uo = oconds[0].enforce(onets[0], *cols)
+    ro = owl.diff_eqs(uo, *cols)[0]
     np.testing.assert_allclose(u.detach().numpy(), uo.detach().numpy().ravel(), rtol=1e-10)
     np.testing.assert_allclose(r.detach().numpy(), ro.detach().numpy().ravel(), rtol=1e-8, atol=1e-10)
 

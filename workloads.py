@@ -253,6 +253,23 @@ def _softplus_net(nd):
                     make_conditions, diff_eqs, 1, 512, _fcnn_flops((1, 16, 16, 1), 2), None)
 
 
+def _biharmonic(nd):
+    """Biharmonic plate  lap(lap u) = 1  on the unit square (DirichletBVP2D): NESTED operators -> fourth-order derivatives of the
+    network output (the reference nests operators the same way, tests/test_operators_identities.py:124-131); autograd path."""
+    def make_nets():
+        return [nd.FCNN(n_input_units=2, n_output_units=1, hidden_units=(16, 16))]
+
+    def make_conditions():
+        return [nd.DirichletBVP2D(x_min=0, x_min_val=lambda y: 0, x_max=1, x_max_val=lambda y: 0,
+                                  y_min=0, y_min_val=lambda x: 0, y_max=1, y_max_val=lambda x: 0)]
+
+    def diff_eqs(u, x, y):
+        return [nd.laplacian(nd.laplacian(u, x, y), x, y) - 1.0]
+
+    return Workload("y3_biharmonic", "Solver2D", ("x", "y"), ((0.0, 1.0), (0.0, 1.0)), [((2, 16, 16, 1), "tanh")], make_nets,
+                    make_conditions, diff_eqs, 1, 512, _fcnn_flops((2, 16, 16, 1), 15), None)
+
+
 _EXTRA = {
     "x1": lambda nd: _heat(nd, "x1_heat_dirichlet_neumann", "right"),
     "x2": lambda nd: _heat(nd, "x2_heat_neumann_dirichlet", "left"),
@@ -269,7 +286,7 @@ NAMES = tuple(_BUILDERS)          # BASELINE.json configs
 EXTRA_NAMES = tuple(_EXTRA)       # widened condition family
 _BUILDERS.update(_EXTRA)
 # problems the fused engine refuses: they run on the autograd path (neurodiffeq_b200/eager.py)
-_FALLBACK = {"y1": _third_order, "y2": _softplus_net}
+_FALLBACK = {"y1": _third_order, "y2": _softplus_net, "y3": _biharmonic}
 FALLBACK_NAMES = tuple(_FALLBACK)
 _BUILDERS.update(_FALLBACK)
 
