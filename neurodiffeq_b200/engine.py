@@ -98,6 +98,20 @@ EXPORTED_SYMBOLS = ("pj_abi_version", "pj_last_error", "pj_sizes", "pj_plan_info
                     "pj_forward_train_jit", "pj_backward_allreduce_bytes", "pj_backward_allreduce", "pj_pack_zero")
 
 
+def planner_refusal(lib, spec, device, n_points=1024):
+    """Text of the planner's refusal if the kernels cannot take this problem at all (return code -2 of ``pj_sizes``: hidden
+    width > PJ_MAX_WIDTH, more than PJ_MAX_NETS output units, jet table too tall, a kernel that does not fit in shared
+    memory, ...), else ``None``.  ``FusedProblem.__init__`` turns it into ``NotImplementedError`` so that the solvers'
+    autograd fallback (eager.py) takes over at construction instead of a ``RuntimeError`` at the first batch."""
+    import contextlib
+    ctx = torch.cuda.device(device) if torch.device(device).type == "cuda" else contextlib.nullcontext()
+    with ctx:
+        rc = lib.pj_sizes(ctypes.byref(spec), n_points, ctypes.byref(PjSizes()))
+    if rc == -2:
+        return lib.pj_last_error().decode()
+    return None
+
+
 def _check(rc, what):
     if rc != 0:
         raise RuntimeError(f"{what} failed ({rc}): {load_library().pj_last_error().decode()}")
@@ -167,6 +181,9 @@ class FusedProblem:
         self._const_coord_cache = {}
         self._adopt_parameters()
         self._build_spec()
+        why = planner_refusal(self.lib, self.spec, self.device)
+        if why is not None:
+            raise NotImplementedError("the kernels' planner refuses this problem: " + why)
         dev = self.device
         self._register_program_scalars()
         self.prog_eval = self._upload(tp.prog_eval)

@@ -190,3 +190,24 @@ def test_autograd_path_matches_reference_golden(key):
     ep.residual_grad(coords)                      # accumulates like loss.backward()
     for g, h in zip(ep.grads_as_list(), gold["grads"]):
         np.testing.assert_allclose(g, 2.0 * h, rtol=1e-9, atol=1e-11 * max(1.0, np.abs(h).max()))
+
+
+def test_planner_refusal_becomes_a_fallback_reason():
+    """engine.planner_refusal: return code -2 of pj_sizes (e.g. hidden width > PJ_MAX_WIDTH) -> text, anything else -> None
+    (other failures keep raising where they always did).  Checked with a stand-in library object: no GPU here."""
+    from neurodiffeq_b200 import engine as E
+
+    class Lib:
+        def __init__(self, rc):
+            self.rc = rc
+
+        def pj_sizes(self, spec, n, out):
+            return self.rc
+
+        def pj_last_error(self):
+            return b"net 0: hidden width 256 not in 1..128"
+
+    spec = E.PjSpec()
+    assert E.planner_refusal(Lib(0), spec, "cpu") is None
+    assert E.planner_refusal(Lib(-4), spec, "cpu") is None
+    assert "hidden width 256" in E.planner_refusal(Lib(-2), spec, "cpu")
