@@ -198,6 +198,14 @@ class FusedProblem:
         self.kernel_launches = 0
         self._graphs = {}
         self._jit, self._jit_ok, self.jit_reason = None, {}, "not requested"
+        # program-length limits of the kernels (pinnjet_api.cu: PROG_MAX, TC_PROG_RESERVE), checked here so that a residual the
+        # kernels cannot hold is a fallback reason at construction rather than an error at the first batch
+        longest = max(len(tp.prog_eval), len(tp.prog_train), len(tp.prog_train_ext))
+        if longest > 1024:
+            raise NotImplementedError(f"residual program of {longest} instructions (the kernels hold 1024)")
+        if (longest + (len(tp.prog_w) if tp.wl else 0)) * 16 > 8192 and self.plan_info(1024).get("tc"):
+            raise NotImplementedError(f"residual program of {longest} instructions is too long for the tensor-core forward kernel "
+                                      f"(PINNJET_TC=0 runs this problem on the FFMA kernels)")
         if os.environ.get("PINNJET_JIT") == "1":
             self.enable_jit()
 
